@@ -1,0 +1,183 @@
+/*
+ * pedoni_cuda.h — C ABI of the B200-native social-force backend (libpedoni_cuda.so).
+ *
+ * This is the drop-in boundary for ONE path of qt2/pedoni: the per-timestep pedestrian update that
+ * sits behind the reference's plugin trait
+ *
+ *     pub trait PedestrianModel: Send + Sync            (pedoni-simulator/src/models/mod.rs:13-25)
+ *         fn new(&SimulatorOptions, &Scenario, &Field) -> Self
+ *         fn spawn_pedestrians(&mut self, &Field, Vec<Pedestrian>)
+ *         fn update_states(&mut self, &Scenario, &Field)
+ *         fn list_pedestrians(&self) -> Vec<Pedestrian>
+ *         fn get_pedestrian_count(&self) -> i32
+ *
+ * A third implementation `SocialForceModelCuda` (ffi/) binds exactly these
+ * entry points. Conventions:
+ *   - plain C types only; every pointer argument is caller-owned and borrowed for the duration of
+ *     the call; outputs go to caller-provided buffers with an explicit capacity;
+ *   - every function returns PEDONI_OK (0) or a negative PedoniStatus; the message is available from
+ *     pedoni_last_error(); nothing throws or aborts across the boundary (the reference panics via
+ *     unwrap(), sfm_gpu.rs:51,69,79,127 — the Rust shim turns a non-zero status into panic!);
+ *   - a handle may be used from a thread other than its creator (main.rs:79-97 moves the Simulator
+ *     to a spawned thread) but is not re-entrant: one caller at a time;
+ *   - pedoni_spawn / pedoni_rebuild / pedoni_step only ENQUEUE device work; pedoni_count,
+ *     pedoni_download, pedoni_cell_table and pedoni_synchronize block;
+ *   - there is no CPU fallback: without a CUDA device pedoni_create fails with PEDONI_ERR_CUDA.
+ */
+#ifndef PEDONI_CUDA_H
+#define PEDONI_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEDONI_ABI_VERSION 1
+
+typedef struct PedoniModel PedoniModel;
+
+typedef enum PedoniStatus {
+    PEDONI_OK = 0,
+    PEDONI_ERR_INVALID = -1,     /* bad argument / config */
+    PEDONI_ERR_CUDA = -2,        /* CUDA runtime or driver error (message has the CUDA string) */
+    PEDONI_ERR_STATE = -3,       /* call sequence error (e.g. step with un-rebuilt spawns) */
+    PEDONI_ERR_CAPACITY = -4,    /* caller buffer too small / device buffer overflow */
+    PEDONI_ERR_UNSUPPORTED = -5, /* option the CUDA path does not implement (use_neighbor_grid = 0) */
+    PEDONI_ERR_COMM = -6         /* NCCL failure (multi-GPU slabs) */
+} PedoniStatus;
+
+/* Arithmetic of the force kernel. Cell keys, neighbor sets and the despawn predicate are IEEE-exact
+ * in both modes. */
+typedef enum PedoniMathMode {
+    PEDONI_MATH_STRICT = 0, /* IEEE div/sqrt, no FMA contraction, reference summation order */
+    PEDONI_MATH_FAST = 1    /* MUFU rcp/rsqrt/ex2 approximations + FMA; same summation order */
+} PedoniMathMode;
+
+/*
+ * Creation parameters = the three arguments of PedestrianModel::new (models/mod.rs:14):
+ *   SimulatorOptions  (lib.rs:108-135)  -> neighbor_grid_unit, field_grid_unit, use_neighbor_grid,
+ *                                          use_distance_map        (gpu_work_size is unused, as in
+ *                                          the reference: args.rs:40 vs :47-66)
+ *   Scenario          (scenario.rs:10-27) -> field_size_*, obstacles
+ *   Field             (field.rs:194-205)  -> field_ny/nx, distance_map, potential_maps
+ * plus device placement. Set struct_size = sizeof(PedoniConfig).
+ */
+typedef struct PedoniConfig {
+    uint32_t struct_size;
+    int32_t device;              /* CUDA device ordinal */
+
+    float field_size_x;          /* Scenario.field.size (metres) */
+    float field_size_y;
+    float neighbor_grid_unit;    /* SimulatorOptions.neighbor_grid_unit, default 1.4 */
+    float field_grid_unit;       /* SimulatorOptions.field_grid_unit, default 0.25 (= Field.unit) */
+    int32_t use_neighbor_grid;   /* must be 1; the O(N^2) debugging path (sfm.rs:157-185) is not built */
+    int32_t use_distance_map;    /* 1: distance-map walls (sfm.rs:188-192); 0: segment walls (sfm.rs:193-237) */
+
+    int32_t field_ny;            /* Field.shape.0 */
+    int32_t field_nx;            /* Field.shape.1 */
+    int32_t n_potential_maps;    /* Field.potential_maps.len() == Scenario.waypoints.len() */
+    int32_t n_obstacles;         /* Scenario.obstacles.len() */
+    const float* distance_map;   /* [field_ny * field_nx] row-major (y, x); copied to the device */
+    const float* potential_maps; /* [n_potential_maps * field_ny * field_nx]; copied to the device */
+    const float* obstacles;      /* [n_obstacles * 5]: x0, y0, x1, y1, width; may be NULL if 0 */
+
+    uint32_t capacity;           /* initial agent capacity (0 = default); buffers grow on demand */
+    int32_t math_mode;           /* PedoniMathMode */
+
+    /* Spatial slab decomposition (one handle per GPU / process). slab_count <= 1: whole domain. */
+    int32_t slab_rank;
+    int32_t slab_count;
+
+    void* stream;                /* optional cudaStream_t to enqueue on (NULL: the handle owns one) */
+} PedoniConfig;
+
+int pedoni_abi_version(void);
+
+/* PedestrianModel::new */
+int pedoni_create(const PedoniConfig* config, PedoniModel** out_model);
+void pedoni_destroy(PedoniModel* model);
+
+/* Message of the last failure on this handle (or of the last failed pedoni_create if model == NULL). */
+const char* pedoni_last_error(const PedoniModel* model);
+
+/*
+ * PedestrianModel::spawn_pedestrians, first half (sfm.rs:49-56): append n pedestrians with zero
+ * velocity. desired_speed is an INPUT (the reference draws it from an unseeded global RNG,
+ * sfm.rs:54; the caller draws it so device code stays RNG-free). n may be 0.
+ * On a slab handle every rank is given the same list; a rank keeps the agents whose cell row it owns.
+ */
+int pedoni_spawn(PedoniModel* model, uint32_t n, const float* pos_xy, const uint32_t* destination,
+                 const float* desired_speed);
+
+/*
+ * PedestrianModel::spawn_pedestrians, second half (sfm.rs:58-77): neighbor-grid rebuild.
+ * Cell key = trunc(pos / unit) (neighbor_grid.rs:27), out-of-grid agents are dropped
+ * (neighbor_grid.rs:29), agents with potential <= 0.25 are despawned (sfm.rs:69), survivors are
+ * reordered cell-major, stably within a cell (sfm.rs:66-68), and the cell-start table
+ * `neighbor_grid_indices` (sfm.rs:61-75) is rebuilt.
+ */
+int pedoni_rebuild(PedoniModel* model);
+
+/* PedestrianModel::update_states (sfm.rs:91-255): forces + integration, dt = 0.1 s. */
+int pedoni_step(PedoniModel* model);
+
+/* PedestrianModel::get_pedestrian_count (sfm.rs:267-269). Blocks. Negative = PedoniStatus. */
+int32_t pedoni_count(PedoniModel* model);
+
+/*
+ * PedestrianModel::list_pedestrians (sfm.rs:257-265) plus the model's private columns.
+ * Writes min(count, cap) agents in the model's current order; *n_out = count. pos_xy and
+ * destination are what the trait returns; vel_xy / desired_speed may be NULL. Blocks.
+ * Returns PEDONI_ERR_CAPACITY (after filling cap agents) if cap < count.
+ */
+int pedoni_download(PedoniModel* model, float* pos_xy, uint32_t* destination, float* vel_xy,
+                    float* desired_speed, uint32_t cap, uint32_t* n_out);
+
+/* Replace the whole agent state (parity tests, checkpoint restore). Unsorted: call pedoni_rebuild. */
+int pedoni_upload_state(PedoniModel* model, uint32_t n, const float* pos_xy, const uint32_t* destination,
+                        const float* vel_xy, const float* desired_speed);
+
+/* Neighbor grid shape (neighbor_grid.rs:15-16): *ny = ceil(size_y / unit), *nx = ceil(size_x / unit). */
+int pedoni_grid_shape(const PedoniModel* model, int32_t* ny, int32_t* nx);
+
+/* `neighbor_grid_indices` (sfm.rs:22): ny*nx + 1 exclusive cell starts of the last rebuild. Blocks.
+ * On a slab handle: the rows this rank owns, (row1 - row0) * nx + 1 entries, local offsets. */
+int pedoni_cell_table(PedoniModel* model, uint32_t* indices, uint32_t cap, uint32_t* n_out);
+
+/* Wait for all enqueued work of this handle. */
+int pedoni_synchronize(PedoniModel* model);
+
+/* ---- measurement (bench.py): device-side timers on the handle's own stream ---------------------- */
+
+typedef struct PedoniKernelTimes {
+    /* accumulated since pedoni_profile_reset, milliseconds, measured with CUDA events */
+    double key_ms, histogram_ms, scan_ms, scatter_ms, gather_ms, force_ms, comm_ms;
+    uint64_t key_launches, histogram_launches, scan_launches, scatter_launches, gather_launches,
+        force_launches, comm_launches;
+    uint64_t force_agents; /* agents processed by the timed force launches */
+} PedoniKernelTimes;
+
+int pedoni_profile_enable(PedoniModel* model, int32_t enable); /* per-kernel events; off by default */
+int pedoni_profile_reset(PedoniModel* model);
+int pedoni_profile_read(PedoniModel* model, PedoniKernelTimes* out); /* blocks */
+
+/* Bracket a region with two events on the handle's stream; end blocks and returns elapsed ms. */
+int pedoni_timer_begin(PedoniModel* model);
+int pedoni_timer_end(PedoniModel* model, float* elapsed_ms);
+
+/* ---- multi-GPU slabs (one process per GPU; NCCL send/recv between slab neighbours) -------------- */
+
+/* Rows [*row0, *row1) of the ny-row neighbor grid owned by `rank` of `count` slabs. Pure host. */
+int pedoni_slab_rows(int32_t ny, int32_t count, int32_t rank, int32_t* row0, int32_t* row1);
+
+#define PEDONI_COMM_ID_BYTES 128
+/* Rank 0 creates the NCCL unique id; the host program (torch.distributed, MPI, a socket) hands the
+ * 128 bytes to every rank, which then joins with pedoni_comm_init. */
+int pedoni_comm_unique_id(void* out_id128);
+int pedoni_comm_init(PedoniModel* model, const void* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEDONI_CUDA_H */

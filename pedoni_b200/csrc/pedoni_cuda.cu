@@ -1,0 +1,812 @@
+// pedoni_cuda.cu — C ABI (include/pedoni_cuda.h) over the sm_100a kernels in grid_sort.cuh and
+// force.cuh. One PedoniModel = the reference's `SocialForceModel` (sfm.rs:18-24) living on one GPU.
+//
+// Data layout in HBM (all SoA, coalesced):
+//   two agent buffers buf[0/1], each {pos float2[cap], vel float2[cap], v0 float[cap], dest u32[cap]}
+//   = 24 B/agent/buffer, the reference's PedestrianVec (sfm.rs:26-33). `cur` holds the live state;
+//   rebuild sorts cur(+appended spawns) -> other, step integrates cur -> other; both swap.
+//   keys/ticket/perm u32[cap] sort scratch; cell_count/cell_start u32[cells+1] (neighbor_grid_indices).
+//   Field maps f32 row-major (field.rs:194-205), uploaded once.
+// Populations stay on the device (d_cur_range); the host only tracks upper bounds for grid sizes,
+// so spawn/rebuild/step never synchronise. count/download block.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pedoni_cuda.h"
+#include "force.cuh"
+#include "slab_comm.hpp"
+
+using namespace pedoni;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum KernelKind { kKey = 0, kHistogram, kScan, kScatter, kGather, kForce, kComm, kNumKinds };
+
+struct TimedLaunch {
+    int kind;
+    cudaEvent_t start, stop;
+    uint64_t agents;
+};
+
+}  // namespace
+
+struct PedoniModel {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int math_mode = 0;
+    bool use_distance_map = true;
+
+    GridView grid{};
+    FieldView field{};
+    float* d_distance = nullptr;
+    float* d_potential = nullptr;
+    float* d_edges = nullptr;
+    int n_obstacles = 0;
+    uint32_t n_cells = 0;  // local table cells
+    uint32_t own_begin_cell = 0, own_end_cell = 0;
+
+    AgentArrays buf[2]{};
+    uint32_t cap = 0;
+    int cur = 0;
+    uint32_t cur_upper = 0;  // host upper bound of live agents in buf[cur]
+    AgentArrays app{};       // appended spawns, not yet rebuilt
+    uint32_t app_cap = 0, app_n = 0;
+
+    uint32_t* d_keys = nullptr;
+    uint32_t* d_ticket = nullptr;
+    uint32_t* d_perm = nullptr;
+    uint32_t aux_cap = 0;
+    uint32_t* d_cell_count = nullptr;
+    uint32_t* d_cell_start = nullptr;
+    uint32_t* d_tile_sums = nullptr;
+    uint32_t n_tiles = 0;
+    uint32_t* d_total = nullptr;
+    uint32_t* d_cur_range = nullptr;  // [begin, end) of owned agents in buf[cur]
+    uint32_t* d_error = nullptr;
+    uint32_t* h_pub = nullptr;      // pinned, mapped: [begin, end, error] published by the device
+    uint32_t* h_pub_dev = nullptr;  // device alias of h_pub
+
+    bool keys_fresh = false;   // d_keys[0, cur_upper) describe buf[cur]
+    bool table_valid = false;  // d_cell_start indexes buf[cur]
+    bool ever_rebuilt = false;
+
+    bool profiling = false;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double acc_ms[kNumKinds] = {0};
+    uint64_t acc_launches[kNumKinds] = {0};
+    uint64_t acc_force_agents = 0;
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+
+    pedoni::SlabComm* comm = nullptr;
+    int slab_rank = 0, slab_count = 1;
+
+    std::string last_error;
+};
+
+namespace {
+
+int fail(PedoniModel* m, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (m)
+        m->last_error = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(m, expr)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t err__ = (expr);                                                                        \
+        if (err__ != cudaSuccess)                                                                          \
+            return fail(m, PEDONI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                        __LINE__);                                                                         \
+    } while (0)
+
+inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// f32 helpers with the reference's (glam) formulations, evaluated on the host in plain IEEE fp32
+// (this TU is compiled with -ffp-contract=off for the host pass).
+struct HVec2 {
+    float x, y;
+};
+
+cudaError_t alloc_agents(AgentArrays& a, uint32_t cap) {
+    cudaError_t e;
+    if ((e = cudaMalloc(&a.pos, sizeof(float2) * (size_t)cap)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&a.vel, sizeof(float2) * (size_t)cap)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&a.v0, sizeof(float) * (size_t)cap)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&a.dest, sizeof(uint32_t) * (size_t)cap)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+void free_agents(AgentArrays& a) {
+    cudaFree(a.pos);
+    cudaFree(a.vel);
+    cudaFree(a.v0);
+    cudaFree(a.dest);
+    a = AgentArrays{};
+}
+cudaError_t copy_agents(AgentArrays& dst, const AgentArrays& src, uint32_t n, cudaStream_t s) {
+    cudaError_t e;
+    if (n == 0) return cudaSuccess;
+    if ((e = cudaMemcpyAsync(dst.pos, src.pos, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToDevice, s))) return e;
+    if ((e = cudaMemcpyAsync(dst.vel, src.vel, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToDevice, s))) return e;
+    if ((e = cudaMemcpyAsync(dst.v0, src.v0, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s))) return e;
+    if ((e = cudaMemcpyAsync(dst.dest, src.dest, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s))) return e;
+    return cudaSuccess;
+}
+
+// Grow both state buffers (keeping buf[cur]'s first keep_n entries) and the sort scratch.
+int ensure_capacity(PedoniModel* m, uint32_t need) {
+    if (need > m->cap) {
+        uint32_t ncap = std::max<uint32_t>(need, m->cap + m->cap / 2);
+        ncap = std::max<uint32_t>(ncap, 1024);
+        for (int b = 0; b < 2; ++b) {
+            AgentArrays fresh{};
+            CUDA_TRY(m, alloc_agents(fresh, ncap));
+            if (b == m->cur && m->cap > 0) CUDA_TRY(m, copy_agents(fresh, m->buf[b], m->cap, m->stream));
+            CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+            free_agents(m->buf[b]);
+            m->buf[b] = fresh;
+        }
+        m->cap = ncap;
+    }
+    if (need > m->aux_cap) {
+        uint32_t ncap = std::max<uint32_t>(need, m->aux_cap + m->aux_cap / 2);
+        ncap = std::max<uint32_t>(ncap, 1024);
+        uint32_t* nk = nullptr;
+        CUDA_TRY(m, cudaMalloc(&nk, sizeof(uint32_t) * (size_t)ncap));
+        if (m->d_keys && m->aux_cap)
+            CUDA_TRY(m, cudaMemcpyAsync(nk, m->d_keys, sizeof(uint32_t) * (size_t)m->aux_cap, cudaMemcpyDeviceToDevice,
+                                        m->stream));
+        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+        cudaFree(m->d_keys);
+        cudaFree(m->d_ticket);
+        cudaFree(m->d_perm);
+        m->d_keys = nk;
+        CUDA_TRY(m, cudaMalloc(&m->d_ticket, sizeof(uint32_t) * (size_t)ncap));
+        CUDA_TRY(m, cudaMalloc(&m->d_perm, sizeof(uint32_t) * (size_t)ncap));
+        m->aux_cap = ncap;
+    }
+    return PEDONI_OK;
+}
+
+int ensure_app_capacity(PedoniModel* m, uint32_t need) {
+    if (need <= m->app_cap) return PEDONI_OK;
+    uint32_t ncap = std::max<uint32_t>(need, m->app_cap * 2);
+    ncap = std::max<uint32_t>(ncap, 1024);
+    AgentArrays fresh{};
+    CUDA_TRY(m, alloc_agents(fresh, ncap));
+    CUDA_TRY(m, copy_agents(fresh, m->app, m->app_n, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    free_agents(m->app);
+    m->app = fresh;
+    m->app_cap = ncap;
+    return PEDONI_OK;
+}
+
+// ---- optional per-kernel event timing -----------------------------------------------------------
+cudaEvent_t take_event(PedoniModel* m) {
+    if (!m->event_pool.empty()) {
+        cudaEvent_t e = m->event_pool.back();
+        m->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedTimer {
+    PedoniModel* m;
+    TimedLaunch t{};
+    bool on;
+    ScopedTimer(PedoniModel* m_, int kind, uint64_t agents = 0) : m(m_), on(m_->profiling) {
+        if (!on) return;
+        t.kind = kind;
+        t.agents = agents;
+        t.start = take_event(m);
+        t.stop = take_event(m);
+        cudaEventRecord(t.start, m->stream);
+    }
+    ~ScopedTimer() {
+        if (!on) return;
+        cudaEventRecord(t.stop, m->stream);
+        m->timed.push_back(t);
+    }
+};
+
+int drain_timed(PedoniModel* m) {
+    if (m->timed.empty()) return PEDONI_OK;
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    for (auto& t : m->timed) {
+        float ms = 0.f;
+        CUDA_TRY(m, cudaEventElapsedTime(&ms, t.start, t.stop));
+        m->acc_ms[t.kind] += ms;
+        m->acc_launches[t.kind] += 1;
+        if (t.kind == kForce) m->acc_force_agents += t.agents;
+        m->event_pool.push_back(t.start);
+        m->event_pool.push_back(t.stop);
+    }
+    m->timed.clear();
+    return PEDONI_OK;
+}
+
+// Obstacle -> 4 edges, sfm.rs:194-205, evaluated once on the host with the reference's f32 ops.
+void build_edges(const float* obstacles, int n, std::vector<float>& out) {
+    out.assign((size_t)n * kEdgeFloats, 0.0f);
+    for (int k = 0; k < n; ++k) {
+        const float* o = obstacles + 5 * k;
+        HVec2 v0{o[0], o[1]}, v1{o[2], o[3]};
+        float w = o[4];
+        HVec2 d{v1.x - v0.x, v1.y - v0.y};
+        float h = std::sqrt((d.x * d.x) + (d.y * d.y));
+        // vec2(d.y, -d.x).normalize_or_zero() * w * 0.5
+        HVec2 nn{d.y, -d.x};
+        float rcp = 1.0f / std::sqrt((nn.x * nn.x) + (nn.y * nn.y));
+        if (std::isfinite(rcp) && rcp > 0.0f) {
+            nn.x = nn.x * rcp;
+            nn.y = nn.y * rcp;
+        } else {
+            nn.x = 0.0f;
+            nn.y = 0.0f;
+        }
+        nn.x = nn.x * w * 0.5f;
+        nn.y = nn.y * w * 0.5f;
+        HVec2 lines[4][2] = {
+            {{v0.x + nn.x, v0.y + nn.y}, {v0.x - nn.x, v0.y - nn.y}},
+            {{v1.x + nn.x, v1.y + nn.y}, {v1.x - nn.x, v1.y - nn.y}},
+            {{v0.x + nn.x, v0.y + nn.y}, {v1.x + nn.x, v1.y + nn.y}},
+            {{v0.x - nn.x, v0.y - nn.y}, {v1.x - nn.x, v1.y - nn.y}},
+        };
+        float* e = out.data() + (size_t)k * kEdgeFloats;
+        for (int j = 0; j < 4; ++j) {
+            HVec2 b{lines[j][1].x - lines[j][0].x, lines[j][1].y - lines[j][0].y};
+            e[5 * j + 0] = lines[j][0].x;
+            e[5 * j + 1] = lines[j][0].y;
+            e[5 * j + 2] = b.x;
+            e[5 * j + 3] = b.y;
+            e[5 * j + 4] = (b.x * b.x) + (b.y * b.y);
+        }
+        e[20] = w;
+        e[21] = h;
+    }
+}
+
+SortInput make_sort_input(PedoniModel* m) {
+    SortInput in{};
+    in.nseg = 2;
+    in.seg[0] = Segment{m->buf[m->cur], m->d_cur_range, m->cur_upper};
+    in.seg[1] = Segment{m->app, nullptr, m->app_n};
+    in.prefix[0] = 0;
+    in.prefix[1] = m->cur_upper;
+    in.prefix[2] = m->cur_upper + m->app_n;
+    for (int k = 3; k <= kMaxSegments; ++k) in.prefix[k] = in.prefix[2];
+    return in;
+}
+
+template <Math M, bool D>
+void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem) {
+    force_integrate_kernel<M, D><<<blocks, 128, smem, m->stream>>>(p);
+}
+
+void launch_force(PedoniModel* m, const ForceParams& p) {
+    const uint32_t blocks = div_up(p.count_upper, 128);
+    if (blocks == 0) return;
+    const size_t smem = m->use_distance_map ? 0 : sizeof(float) * 64 * kEdgeFloats;
+    if (m->math_mode == PEDONI_MATH_STRICT) {
+        if (m->use_distance_map)
+            launch_force_t<Math::Strict, true>(m, p, blocks, smem);
+        else
+            launch_force_t<Math::Strict, false>(m, p, blocks, smem);
+    } else {
+        if (m->use_distance_map)
+            launch_force_t<Math::Fast, true>(m, p, blocks, smem);
+        else
+            launch_force_t<Math::Fast, false>(m, p, blocks, smem);
+    }
+}
+
+int check_device_error(PedoniModel* m) {
+    if (m->h_pub[2] != 0) {
+        m->h_pub[2] = 0;
+        cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream);
+        return fail(m, PEDONI_ERR_INVALID,
+                    "device flagged an invalid agent (destination >= n_potential_maps); the reference would panic "
+                    "with an index-out-of-bounds at field.rs:237");
+    }
+    return PEDONI_OK;
+}
+
+__global__ void publish_error_kernel(const uint32_t* d_error, uint32_t* h_slot) { *h_slot = *d_error; }
+
+__global__ void set_range_kernel(uint32_t* d_range, uint32_t* host_slot, uint32_t b, uint32_t e) {
+    d_range[0] = b;
+    d_range[1] = e;
+    host_slot[0] = b;
+    host_slot[1] = e;
+}
+
+}  // namespace
+
+// ===================================================================================================
+extern "C" {
+
+int pedoni_abi_version(void) { return PEDONI_ABI_VERSION; }
+
+const char* pedoni_last_error(const PedoniModel* model) {
+    return model ? model->last_error.c_str() : g_create_error.c_str();
+}
+
+int pedoni_slab_rows(int32_t ny, int32_t count, int32_t rank, int32_t* row0, int32_t* row1) {
+    if (ny <= 0 || count <= 0 || rank < 0 || rank >= count || !row0 || !row1) return PEDONI_ERR_INVALID;
+    // Balanced contiguous row ranges; the first (ny % count) slabs get one extra row.
+    int32_t base = ny / count, extra = ny % count;
+    *row0 = rank * base + std::min(rank, extra);
+    *row1 = *row0 + base + (rank < extra ? 1 : 0);
+    return PEDONI_OK;
+}
+
+int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
+    if (!c || !out) return fail(nullptr, PEDONI_ERR_INVALID, "null config or out pointer");
+    *out = nullptr;
+    if (c->struct_size != sizeof(PedoniConfig))
+        return fail(nullptr, PEDONI_ERR_INVALID, "PedoniConfig.struct_size %u != %zu (ABI mismatch)", c->struct_size,
+                    sizeof(PedoniConfig));
+    if (!c->use_neighbor_grid)
+        return fail(nullptr, PEDONI_ERR_UNSUPPORTED,
+                    "use_neighbor_grid = false (the O(N^2) path, sfm.rs:157-185) is not implemented on CUDA");
+    if (!(c->neighbor_grid_unit > 0.f) || !(c->field_grid_unit > 0.f))
+        return fail(nullptr, PEDONI_ERR_INVALID, "grid units must be positive");
+    if (c->field_ny <= 0 || c->field_nx <= 0 || c->n_potential_maps <= 0 || !c->distance_map || !c->potential_maps)
+        return fail(nullptr, PEDONI_ERR_INVALID, "field maps missing or empty");
+    if (c->n_obstacles < 0 || (c->n_obstacles > 0 && !c->obstacles))
+        return fail(nullptr, PEDONI_ERR_INVALID, "obstacles pointer missing");
+    if (c->math_mode != PEDONI_MATH_STRICT && c->math_mode != PEDONI_MATH_FAST)
+        return fail(nullptr, PEDONI_ERR_INVALID, "unknown math_mode %d", c->math_mode);
+
+    int n_dev = 0;
+    cudaError_t err = cudaGetDeviceCount(&n_dev);
+    if (err != cudaSuccess || n_dev == 0)
+        return fail(nullptr, PEDONI_ERR_CUDA, "no CUDA device available (%s); there is no CPU fallback",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+    if (c->device < 0 || c->device >= n_dev)
+        return fail(nullptr, PEDONI_ERR_INVALID, "device %d out of range [0, %d)", c->device, n_dev);
+
+    PedoniModel* m = new PedoniModel();
+    auto bail = [&](int code) {
+        g_create_error = m->last_error;
+        pedoni_destroy(m);
+        return code;
+    };
+#define CREATE_TRY(expr)                                                                                \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            fail(m, PEDONI_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));                  \
+            return bail(PEDONI_ERR_CUDA);                                                               \
+        }                                                                                               \
+    } while (0)
+
+    m->device = c->device;
+    CREATE_TRY(cudaSetDevice(m->device));
+    if (c->stream) {
+        m->stream = static_cast<cudaStream_t>(c->stream);
+    } else {
+        CREATE_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->own_stream = true;
+    }
+    m->math_mode = c->math_mode;
+    m->use_distance_map = c->use_distance_map != 0;
+
+    // neighbor_grid.rs:14-17: shape = ceil(size / unit) as (ny, nx)
+    const float gx = std::ceil(c->field_size_x / c->neighbor_grid_unit);
+    const float gy = std::ceil(c->field_size_y / c->neighbor_grid_unit);
+    if (!(gx >= 1.f) || !(gy >= 1.f) || gx * gy > 2.0e9f) {
+        fail(m, PEDONI_ERR_INVALID, "neighbor grid %g x %g is empty or too large", gx, gy);
+        return bail(PEDONI_ERR_INVALID);
+    }
+    m->grid.unit = c->neighbor_grid_unit;
+    m->grid.nx = static_cast<int>(gx);
+    m->grid.ny = static_cast<int>(gy);
+
+    m->slab_count = c->slab_count > 1 ? c->slab_count : 1;
+    m->slab_rank = m->slab_count > 1 ? c->slab_rank : 0;
+    int32_t r0 = 0, r1 = m->grid.ny;
+    if (m->slab_count > 1) {
+        if (pedoni_slab_rows(m->grid.ny, m->slab_count, m->slab_rank, &r0, &r1) != PEDONI_OK || r1 - r0 < 1) {
+            fail(m, PEDONI_ERR_INVALID, "slab %d of %d owns no rows of a %d-row grid", m->slab_rank, m->slab_count,
+                 m->grid.ny);
+            return bail(PEDONI_ERR_INVALID);
+        }
+    }
+    m->grid.own_row0 = r0;
+    m->grid.own_row1 = r1;
+    m->grid.row_base = std::max(r0 - 1, 0);
+    const int table_end = std::min(r1 + 1, m->grid.ny);
+    m->grid.table_rows = table_end - m->grid.row_base;
+    m->n_cells = static_cast<uint32_t>(m->grid.table_rows) * static_cast<uint32_t>(m->grid.nx);
+    m->own_begin_cell = static_cast<uint32_t>(r0 - m->grid.row_base) * m->grid.nx;
+    m->own_end_cell = static_cast<uint32_t>(r1 - m->grid.row_base) * m->grid.nx;
+
+    // Field (field.rs:194-205)
+    m->field.unit = c->field_grid_unit;
+    m->field.fy = c->field_ny;
+    m->field.fx = c->field_nx;
+    m->field.n_maps = c->n_potential_maps;
+    const size_t map_elems = static_cast<size_t>(c->field_ny) * c->field_nx;
+    CREATE_TRY(cudaMalloc(&m->d_distance, map_elems * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&m->d_potential, map_elems * sizeof(float) * c->n_potential_maps));
+    CREATE_TRY(cudaMemcpyAsync(m->d_distance, c->distance_map, map_elems * sizeof(float), cudaMemcpyHostToDevice,
+                               m->stream));
+    CREATE_TRY(cudaMemcpyAsync(m->d_potential, c->potential_maps, map_elems * sizeof(float) * c->n_potential_maps,
+                               cudaMemcpyHostToDevice, m->stream));
+    m->field.distance_map = m->d_distance;
+    m->field.potential_maps = m->d_potential;
+
+    m->n_obstacles = c->n_obstacles;
+    if (!m->use_distance_map && m->n_obstacles > 0) {
+        std::vector<float> edges;
+        build_edges(c->obstacles, c->n_obstacles, edges);
+        CREATE_TRY(cudaMalloc(&m->d_edges, edges.size() * sizeof(float)));
+        CREATE_TRY(cudaMemcpyAsync(m->d_edges, edges.data(), edges.size() * sizeof(float), cudaMemcpyHostToDevice,
+                                   m->stream));
+        CREATE_TRY(cudaStreamSynchronize(m->stream));  // `edges` dies at scope end
+    }
+
+    // cell table + scan scratch
+    m->n_tiles = div_up(m->n_cells, kScanTile);
+    CREATE_TRY(cudaMalloc(&m->d_cell_count, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
+    CREATE_TRY(cudaMalloc(&m->d_cell_start, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
+    CREATE_TRY(cudaMalloc(&m->d_tile_sums, sizeof(uint32_t) * std::max<uint32_t>(m->n_tiles, 1)));
+    CREATE_TRY(cudaMalloc(&m->d_total, sizeof(uint32_t)));
+    CREATE_TRY(cudaMalloc(&m->d_cur_range, sizeof(uint32_t) * 2));
+    CREATE_TRY(cudaMalloc(&m->d_error, sizeof(uint32_t)));
+    CREATE_TRY(cudaMemsetAsync(m->d_cell_start, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
+    CREATE_TRY(cudaMemsetAsync(m->d_cur_range, 0, sizeof(uint32_t) * 2, m->stream));
+    CREATE_TRY(cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
+    CREATE_TRY(cudaHostAlloc(&m->h_pub, sizeof(uint32_t) * 4, cudaHostAllocMapped));
+    std::memset(m->h_pub, 0, sizeof(uint32_t) * 4);
+    CREATE_TRY(cudaHostGetDevicePointer(&m->h_pub_dev, m->h_pub, 0));
+    CREATE_TRY(cudaEventCreate(&m->timer_start));
+    CREATE_TRY(cudaEventCreate(&m->timer_stop));
+
+    if (ensure_capacity(m, c->capacity ? c->capacity : 4096) != PEDONI_OK) return bail(PEDONI_ERR_CUDA);
+    CREATE_TRY(cudaStreamSynchronize(m->stream));  // borrowed map pointers may die after return
+#undef CREATE_TRY
+    *out = m;
+    return PEDONI_OK;
+}
+
+void pedoni_destroy(PedoniModel* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->comm) pedoni::slab_comm_destroy(m->comm);
+    for (auto& t : m->timed) {
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    for (auto e : m->event_pool) cudaEventDestroy(e);
+    if (m->timer_start) cudaEventDestroy(m->timer_start);
+    if (m->timer_stop) cudaEventDestroy(m->timer_stop);
+    free_agents(m->buf[0]);
+    free_agents(m->buf[1]);
+    free_agents(m->app);
+    cudaFree(m->d_keys);
+    cudaFree(m->d_ticket);
+    cudaFree(m->d_perm);
+    cudaFree(m->d_cell_count);
+    cudaFree(m->d_cell_start);
+    cudaFree(m->d_tile_sums);
+    cudaFree(m->d_total);
+    cudaFree(m->d_cur_range);
+    cudaFree(m->d_error);
+    cudaFree(m->d_distance);
+    cudaFree(m->d_potential);
+    cudaFree(m->d_edges);
+    if (m->h_pub) cudaFreeHost(m->h_pub);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int pedoni_synchronize(PedoniModel* m) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return check_device_error(m);
+}
+
+static int append_agents(PedoniModel* m, uint32_t n, const float* pos_xy, const uint32_t* dest, const float* vel_xy,
+                         const float* v0) {
+    if (n == 0) return PEDONI_OK;
+    if (!pos_xy || !dest || !v0) return fail(m, PEDONI_ERR_INVALID, "null agent array with n = %u", n);
+    if ((uint64_t)m->cur_upper + m->app_n + n > 0xFFFFFFF0ull) return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
+    int rc = ensure_app_capacity(m, m->app_n + n);
+    if (rc != PEDONI_OK) return rc;
+    const uint32_t at = m->app_n;
+    CUDA_TRY(m, cudaMemcpyAsync(m->app.pos + at, pos_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(m, cudaMemcpyAsync(m->app.dest + at, dest, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(m, cudaMemcpyAsync(m->app.v0 + at, v0, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    if (vel_xy)
+        CUDA_TRY(m, cudaMemcpyAsync(m->app.vel + at, vel_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice,
+                                    m->stream));
+    else  // sfm.rs:53 velocity: Vec2::ZERO
+        CUDA_TRY(m, cudaMemsetAsync(m->app.vel + at, 0, sizeof(float2) * (size_t)n, m->stream));
+    // Pageable sources are staged before cudaMemcpyAsync returns; pinned sources are read
+    // asynchronously, and the caller's buffers are only borrowed for the call -> wait.
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, pos_xy) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered)
+        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    (void)cudaGetLastError();
+    m->app_n += n;
+    m->table_valid = false;
+    return PEDONI_OK;
+}
+
+int pedoni_spawn(PedoniModel* m, uint32_t n, const float* pos_xy, const uint32_t* dest, const float* v0) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    return append_agents(m, n, pos_xy, dest, nullptr, v0);
+}
+
+int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const uint32_t* dest, const float* vel_xy,
+                        const float* v0) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (n > 0 && !vel_xy) return fail(m, PEDONI_ERR_INVALID, "null velocity array");
+    set_range_kernel<<<1, 1, 0, m->stream>>>(m->d_cur_range, m->h_pub_dev, 0u, 0u);
+    m->cur_upper = 0;
+    m->app_n = 0;
+    m->keys_fresh = false;
+    m->table_valid = false;
+    return append_agents(m, n, pos_xy, dest, vel_xy, v0);
+}
+
+int pedoni_rebuild(PedoniModel* m) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    const uint32_t total = m->cur_upper + m->app_n;
+    int rc = ensure_capacity(m, std::max<uint32_t>(total, 1));
+    if (rc != PEDONI_OK) return rc;
+    cudaStream_t s = m->stream;
+    SortInput in = make_sort_input(m);
+
+    if (total > 0) {
+        const uint32_t t_begin = m->keys_fresh ? m->cur_upper : 0u;
+        if (t_begin < total) {
+            ScopedTimer t(m, kKey);
+            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field, m->d_keys,
+                                                                   m->d_error, /*foreign_rows_drop=*/true);
+        }
+    }
+    {
+        ScopedTimer t(m, kHistogram);
+        CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
+        if (total > 0)
+            histogram_kernel<<<div_up(total, 256), 256, 0, s>>>(total, m->d_keys, m->d_cell_count, m->d_ticket);
+    }
+    {
+        ScopedTimer t(m, kScan);
+        scan_reduce_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums);
+        scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(m->d_tile_sums, m->n_tiles, m->d_total);
+        scan_apply_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums,
+                                                              m->d_cell_start);
+    }
+    if (total > 0) {
+        {
+            ScopedTimer t(m, kScatter);
+            scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(total, m->d_keys, m->d_ticket, m->d_cell_start, m->d_perm);
+        }
+        {
+            ScopedTimer t(m, kGather);
+            gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_keys, m->d_cell_start, m->d_perm,
+                                                            m->buf[m->cur ^ 1]);
+        }
+    }
+    publish_range_kernel<<<1, 1, 0, s>>>(m->d_cell_start, m->own_begin_cell, m->own_end_cell, m->d_cur_range,
+                                         m->h_pub_dev);
+    publish_error_kernel<<<1, 1, 0, s>>>(m->d_error, m->h_pub_dev + 2);
+    CUDA_TRY(m, cudaGetLastError());
+
+    m->cur ^= 1;
+    m->cur_upper = total;
+    m->app_n = 0;
+    m->keys_fresh = false;
+    m->table_valid = true;
+    m->ever_rebuilt = true;
+    return PEDONI_OK;
+}
+
+int pedoni_step(PedoniModel* m) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (m->app_n > 0 || !m->table_valid)
+        return fail(m, PEDONI_ERR_STATE,
+                    "pedoni_step needs a rebuilt neighbor grid: call pedoni_rebuild after pedoni_spawn / "
+                    "pedoni_upload_state (the reference rebuilds inside spawn_pedestrians, sfm.rs:58-77)");
+    if (m->cur_upper > 0) {
+        ForceParams p{};
+        p.in = m->buf[m->cur];
+        p.out = m->buf[m->cur ^ 1];
+        p.d_range = m->d_cur_range;
+        p.first = 0;
+        p.count_upper = m->cur_upper;
+        p.cell_start = m->d_cell_start;
+        p.grid = m->grid;
+        p.field = m->field;
+        p.keys_out = m->d_keys;
+        p.key_base = 0;
+        p.error_flag = m->d_error;
+        p.obstacle_edges = m->d_edges;
+        p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
+        ScopedTimer t(m, kForce, m->cur_upper);
+        launch_force(m, p);
+    }
+    CUDA_TRY(m, cudaGetLastError());
+    m->cur ^= 1;
+    m->keys_fresh = true;
+    return PEDONI_OK;
+}
+
+// Blocks; refreshes the host's knowledge of the live range.
+static int sync_range(PedoniModel* m, uint32_t* begin, uint32_t* end) {
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    int rc = check_device_error(m);
+    if (rc != PEDONI_OK) return rc;
+    *begin = m->h_pub[0];
+    *end = m->h_pub[1];
+    return PEDONI_OK;
+}
+
+int32_t pedoni_count(PedoniModel* m) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    uint32_t b, e;
+    int rc = sync_range(m, &b, &e);
+    if (rc != PEDONI_OK) return rc;
+    return static_cast<int32_t>(e - b + m->app_n);
+}
+
+int pedoni_download(PedoniModel* m, float* pos_xy, uint32_t* dest, float* vel_xy, float* v0, uint32_t cap,
+                    uint32_t* n_out) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    uint32_t b, e;
+    int rc = sync_range(m, &b, &e);
+    if (rc != PEDONI_OK) return rc;
+    const uint32_t n_cur = e - b, n = n_cur + m->app_n;
+    if (n_out) *n_out = n;
+    const uint32_t take_cur = std::min(n_cur, cap), take_app = std::min(m->app_n, cap - take_cur);
+    const AgentArrays& a = m->buf[m->cur];
+    auto pull = [&](void* dst, const void* src_cur, const void* src_app, size_t elem) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        cudaError_t er = cudaSuccess;
+        if (take_cur)
+            er = cudaMemcpyAsync(dst, static_cast<const char*>(src_cur) + elem * b, elem * take_cur,
+                                 cudaMemcpyDeviceToHost, m->stream);
+        if (er == cudaSuccess && take_app)
+            er = cudaMemcpyAsync(static_cast<char*>(dst) + elem * take_cur, src_app, elem * take_app,
+                                 cudaMemcpyDeviceToHost, m->stream);
+        return er;
+    };
+    CUDA_TRY(m, pull(pos_xy, a.pos, m->app.pos, sizeof(float2)));
+    CUDA_TRY(m, pull(dest, a.dest, m->app.dest, sizeof(uint32_t)));
+    CUDA_TRY(m, pull(vel_xy, a.vel, m->app.vel, sizeof(float2)));
+    CUDA_TRY(m, pull(v0, a.v0, m->app.v0, sizeof(float)));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    if (cap < n) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", cap, n);
+    return PEDONI_OK;
+}
+
+int pedoni_grid_shape(const PedoniModel* m, int32_t* ny, int32_t* nx) {
+    if (!m || !ny || !nx) return PEDONI_ERR_INVALID;
+    *ny = m->grid.ny;
+    *nx = m->grid.nx;
+    return PEDONI_OK;
+}
+
+int pedoni_cell_table(PedoniModel* m, uint32_t* indices, uint32_t cap, uint32_t* n_out) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (!m->ever_rebuilt) return fail(m, PEDONI_ERR_STATE, "no rebuild yet");
+    const uint32_t n = m->own_end_cell - m->own_begin_cell + 1;
+    if (n_out) *n_out = n;
+    if (cap < n || !indices) return fail(m, PEDONI_ERR_CAPACITY, "cell table needs %u entries", n);
+    CUDA_TRY(m, cudaMemcpyAsync(indices, m->d_cell_start + m->own_begin_cell, sizeof(uint32_t) * (size_t)n,
+                                cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    const uint32_t base = indices[0];  // local offsets: halo agents below the owned rows do not count
+    if (base)
+        for (uint32_t k = 0; k < n; ++k) indices[k] -= base;
+    return PEDONI_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------
+int pedoni_profile_enable(PedoniModel* m, int32_t enable) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    int rc = drain_timed(m);
+    m->profiling = enable != 0;
+    return rc;
+}
+int pedoni_profile_reset(PedoniModel* m) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    int rc = drain_timed(m);
+    for (int k = 0; k < kNumKinds; ++k) {
+        m->acc_ms[k] = 0;
+        m->acc_launches[k] = 0;
+    }
+    m->acc_force_agents = 0;
+    return rc;
+}
+int pedoni_profile_read(PedoniModel* m, PedoniKernelTimes* out) {
+    if (!m || !out) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    int rc = drain_timed(m);
+    if (rc != PEDONI_OK) return rc;
+    out->key_ms = m->acc_ms[kKey];
+    out->histogram_ms = m->acc_ms[kHistogram];
+    out->scan_ms = m->acc_ms[kScan];
+    out->scatter_ms = m->acc_ms[kScatter];
+    out->gather_ms = m->acc_ms[kGather];
+    out->force_ms = m->acc_ms[kForce];
+    out->comm_ms = m->acc_ms[kComm];
+    out->key_launches = m->acc_launches[kKey];
+    out->histogram_launches = m->acc_launches[kHistogram];
+    out->scan_launches = m->acc_launches[kScan];
+    out->scatter_launches = m->acc_launches[kScatter];
+    out->gather_launches = m->acc_launches[kGather];
+    out->force_launches = m->acc_launches[kForce];
+    out->comm_launches = m->acc_launches[kComm];
+    out->force_agents = m->acc_force_agents;
+    return PEDONI_OK;
+}
+int pedoni_timer_begin(PedoniModel* m) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    CUDA_TRY(m, cudaEventRecord(m->timer_start, m->stream));
+    return PEDONI_OK;
+}
+int pedoni_timer_end(PedoniModel* m, float* ms) {
+    if (!m || !ms) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    CUDA_TRY(m, cudaEventRecord(m->timer_stop, m->stream));
+    CUDA_TRY(m, cudaEventSynchronize(m->timer_stop));
+    CUDA_TRY(m, cudaEventElapsedTime(ms, m->timer_start, m->timer_stop));
+    return PEDONI_OK;
+}
+
+// ---- multi-GPU slabs ------------------------------------------------------------------------------
+int pedoni_comm_unique_id(void* out_id128) {
+    std::string err;
+    int rc = pedoni::slab_comm_unique_id(out_id128, &err);
+    if (rc != PEDONI_OK) g_create_error = err;
+    return rc;
+}
+int pedoni_comm_init(PedoniModel* m, const void* id128) {
+    if (!m || !id128) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (m->slab_count <= 1) return fail(m, PEDONI_ERR_STATE, "pedoni_comm_init on a whole-domain handle");
+    std::string err;
+    m->comm = pedoni::slab_comm_create(id128, m->slab_rank, m->slab_count, &err);
+    if (!m->comm) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
+    return PEDONI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// sfm_device.cuh — device-side arithmetic shared by the grid-sort and force kernels (sm_100a).
+//
+// Two arithmetic modes (include/pedoni_cuda.h PedoniMathMode):
+//   Strict : every op is an IEEE round-to-nearest intrinsic (__fadd_rn, __fmul_rn, __fdiv_rn,
+//            __fsqrt_rn) so nvcc cannot contract a*b+c into FMA — the Rust reference never fuses.
+//            exp is evaluated in fp64 and rounded once, which reproduces glibc's (correctly rounded
+//            in all but ~1e-9 of cases) expf that the reference calls through f32::exp.
+//   Fast   : MUFU-based rcp / rsqrt / sqrt / ex2 approximations, FMA contraction allowed.
+// Cell keys, the despawn predicate and all field sampling are Strict in BOTH modes: cell assignment
+// and neighbor sets must be bit-exact given identical positions (neighbor_grid.rs:27, sfm.rs:69).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pedoni {
+
+enum class Math : int { Strict = 0, Fast = 1 };
+
+template <Math M>
+struct Ops;
+
+template <>
+struct Ops<Math::Strict> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ float rcp(float a) { return __fdiv_rn(1.0f, a); }
+    static __device__ __forceinline__ float exp(float a) { return static_cast<float>(::exp(static_cast<double>(a))); }
+};
+
+template <>
+struct Ops<Math::Fast> {
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) {
+        float r;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+        return r;
+    }
+    static __device__ __forceinline__ float rcp(float a) {
+        float r;
+        asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+        return r;
+    }
+    static __device__ __forceinline__ float exp(float a) { return __expf(a); }
+};
+
+using S = Ops<Math::Strict>;
+
+// ------------------------------------------------------------------------------------------------
+// Field samplers — util.rs:44-58 `bilinear`, util.rs:61-75 `sobel_filter`, field.rs:235-258.
+// Maps are row-major (y, x) f32 (ndarray Array2 of shape (fy, fx), util.rs:29-40). An out-of-bounds
+// tap reads 1e12 (util.rs:45,53-56). No texture hardware: the reference's own OpenCL path uses it
+// (sfm_gpu.cl:4-5) and diverges from the CPU model (9-bit weights, clamp addressing).
+// ------------------------------------------------------------------------------------------------
+struct FieldView {
+    float unit;
+    int fy, fx;
+    int n_maps;
+    const float* __restrict__ distance_map;
+    const float* __restrict__ potential_maps;
+};
+
+__device__ __forceinline__ float field_tap(const float* __restrict__ g, int ny, int nx, int x, int y) {
+    return (x >= 0 && y >= 0 && x < nx && y < ny) ? __ldg(g + static_cast<size_t>(y) * nx + x) : 1e12f;
+}
+
+// One axis of `bilinear`'s setup for p: base = floor(p); t = p - base; s = 1 - t; i = base as i32.
+struct Axis {
+    float t, s;
+    int i;
+};
+__device__ __forceinline__ Axis axis_of(float p) {
+    float base = floorf(p);
+    Axis a;
+    a.t = S::sub(p, base);
+    a.s = S::sub(1.0f, a.t);
+    a.i = __float2int_rz(base);  // cvt.rzi.s32.f32: saturating, NaN -> 0 == Rust `as i32`
+    return a;
+}
+
+// util.rs:52-57, taps g00=(ix,iy) g01=(ix+1,iy) g10=(ix,iy+1) g11=(ix+1,iy+1).
+__device__ __forceinline__ float bilinear_combine(const Axis& ax, const Axis& ay, float g00, float g01, float g10,
+                                                  float g11) {
+    float y = 0.0f;
+    y = S::add(y, S::mul(S::mul(ay.s, ax.s), g00));
+    y = S::add(y, S::mul(S::mul(ay.s, ax.t), g01));
+    y = S::add(y, S::mul(S::mul(ay.t, ax.s), g10));
+    y = S::add(y, S::mul(S::mul(ay.t, ax.t), g11));
+    return y;
+}
+
+__device__ __forceinline__ float bilinear(const float* __restrict__ g, int ny, int nx, float px, float py) {
+    Axis ax = axis_of(px), ay = axis_of(py);
+    return bilinear_combine(ax, ay, field_tap(g, ny, nx, ax.i, ay.i), field_tap(g, ny, nx, ax.i + 1, ay.i),
+                            field_tap(g, ny, nx, ax.i, ay.i + 1), field_tap(g, ny, nx, ax.i + 1, ay.i + 1));
+}
+
+// `position / unit - 0.5` (field.rs:236,243,250,256): true divide, then subtract.
+__device__ __forceinline__ float2 field_coord(float2 pos, float unit) {
+    return make_float2(S::sub(S::div(pos.x, unit), 0.5f), S::sub(S::div(pos.y, unit), 0.5f));
+}
+
+// field.rs:235-239
+__device__ __forceinline__ float get_potential(const FieldView& f, uint32_t waypoint, float2 pos) {
+    float2 q = field_coord(pos, f.unit);
+    return bilinear(f.potential_maps + static_cast<size_t>(waypoint) * f.fy * f.fx, f.fy, f.fx, q.x, q.y);
+}
+
+// Sobel gradient of the bilinear interpolant at q (util.rs:61-75), optionally also the centre
+// sample (field.rs:242-245 for the wall term). The nine bilinear evaluations of the reference touch
+// a 4x4 texel footprint; the common case (consecutive bases, footprint inside the map) loads those
+// 16 texels once. Each of the 8 (9) samples is then combined with exactly the reference's
+// per-sample weights and operation order, so the result is bit-identical to 8 (9) independent
+// `bilinear` calls. Rounding in `q + 1.0` can make bases non-consecutive; that and the map border
+// take the generic path.
+template <bool WithCentre>
+__device__ __forceinline__ void sobel_sample(const float* __restrict__ g, int ny, int nx, float2 q, float& gx,
+                                             float& gy, float& centre) {
+    Axis ax[3], ay[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        ax[o] = axis_of(S::add(q.x, static_cast<float>(o - 1)));
+        ay[o] = axis_of(S::add(q.y, static_cast<float>(o - 1)));
+    }
+    float u[3][3];  // u[r][c]: r = y offset + 1, c = x offset + 1 (util.rs:62-69)
+    const int x0 = ax[0].i, y0 = ay[0].i;
+    const bool consecutive = (ax[1].i == x0 + 1) && (ax[2].i == x0 + 2) && (ay[1].i == y0 + 1) && (ay[2].i == y0 + 2);
+    const bool inside = x0 >= 0 && y0 >= 0 && x0 + 3 < nx && y0 + 3 < ny;
+    if (consecutive && inside) {
+        float tex[4][4];
+        const float* base = g + static_cast<size_t>(y0) * nx + x0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tex[r][c] = __ldg(base + static_cast<size_t>(r) * nx + c);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!WithCentre && r == 1 && c == 1) continue;
+                u[r][c] = bilinear_combine(ax[c], ay[r], tex[r][c], tex[r][c + 1], tex[r + 1][c], tex[r + 1][c + 1]);
+            }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!WithCentre && r == 1 && c == 1) continue;
+                u[r][c] = bilinear_combine(ax[c], ay[r], field_tap(g, ny, nx, ax[c].i, ay[r].i),
+                                           field_tap(g, ny, nx, ax[c].i + 1, ay[r].i),
+                                           field_tap(g, ny, nx, ax[c].i, ay[r].i + 1),
+                                           field_tap(g, ny, nx, ax[c].i + 1, ay[r].i + 1));
+            }
+    }
+    // util.rs:72-73, left to right.
+    gx = S::sub(S::sub(S::sub(S::sub(S::add(S::add(S::add(u[0][0], u[1][0]), u[1][0]), u[2][0]), u[0][2]), u[1][2]),
+                       u[1][2]),
+                u[2][2]);
+    gy = S::sub(S::sub(S::sub(S::sub(S::add(S::add(S::add(u[0][0], u[0][1]), u[0][1]), u[0][2]), u[2][0]), u[2][1]),
+                       u[2][1]),
+                u[2][2]);
+    centre = WithCentre ? u[1][1] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbor grid — neighbor_grid.rs:14-36, util.rs:29-36.
+// ------------------------------------------------------------------------------------------------
+struct GridView {
+    float unit;      // neighbor_grid_unit
+    int nx, ny;      // global grid shape (neighbor_grid.rs:15-16)
+    int row_base;    // global row of local table row 0 (0 on a whole-domain handle)
+    int table_rows;  // rows covered by the local cell table (ny on a whole-domain handle)
+    int own_row0;    // global rows [own_row0, own_row1) are owned by this handle
+    int own_row1;
+};
+
+constexpr uint32_t kKeyDrop = 0xFFFFFFFFu;         // out of grid, despawned, or not ours
+constexpr uint32_t kKeyMigrateDown = 0xFFFFFFFEu;  // alive, now in a row below own_row0 (slabs)
+constexpr uint32_t kKeyMigrateUp = 0xFFFFFFFDu;    // alive, now in a row >= own_row1 (slabs)
+constexpr uint32_t kKeyFirstSpecial = 0xFFFFFFF0u;
+
+// `(pos / unit).as_ivec2()` (neighbor_grid.rs:27, sfm.rs:113): IEEE divide, truncate toward zero.
+__device__ __forceinline__ int2 cell_of(float2 pos, float unit) {
+    return make_int2(__float2int_rz(S::div(pos.x, unit)), __float2int_rz(S::div(pos.y, unit)));
+}
+
+// Sort key of an agent for the next rebuild: local cell id, or a special.
+//  - outside the grid -> dropped (neighbor_grid.rs:29-33, util.rs:31)
+//  - potential(dest, pos) > 0.25 is false (incl. NaN) -> despawned (sfm.rs:69)
+//  - destination >= n_maps would panic in the reference (index out of bounds); here it drops the
+//    agent and raises the device error flag.
+__device__ __forceinline__ uint32_t sort_key(const GridView& g, const FieldView& f, float2 pos, uint32_t dest,
+                                             uint32_t* error_flag) {
+    int2 c = cell_of(pos, g.unit);
+    if (c.x < 0 || c.y < 0 || c.x >= g.nx || c.y >= g.ny) return kKeyDrop;
+    if (dest >= static_cast<uint32_t>(f.n_maps)) {
+        atomicOr(error_flag, 1u);
+        return kKeyDrop;
+    }
+    if (!(get_potential(f, dest, pos) > 0.25f)) return kKeyDrop;
+    if (c.y < g.own_row0) return kKeyMigrateDown;
+    if (c.y >= g.own_row1) return kKeyMigrateUp;
+    return static_cast<uint32_t>(c.y - g.row_base) * static_cast<uint32_t>(g.nx) + static_cast<uint32_t>(c.x);
+}
+
+}  // namespace pedoni

@@ -1,0 +1,210 @@
+"""`SocialForceModelCuda` — harness-side mirror of the reference's `PedestrianModel` plugin trait
+(pedoni-simulator/src/models/mod.rs:13-25) over the C ABI in include/pedoni_cuda.h.
+
+Same method names, argument meaning and error behaviour as the Rust trait: methods do not return
+errors; a failing C-ABI call raises (the Rust shim panics, like the reference's unwrap()s at
+sfm_gpu.rs:51,69,79,127).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+
+
+@dataclass
+class Pedestrian:
+    """models/mod.rs:28-32 `Pedestrian { pos: Vec2, destination: usize }`."""
+    pos: tuple
+    destination: int = 0
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _fp(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(_capi.c_float_p) if a is not None else None
+
+
+def _up(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(_capi.c_u32_p) if a is not None else None
+
+
+class SocialForceModelCuda:
+    """Third `PedestrianModel` implementation (after sfm.rs `SocialForceModel` and sfm_gpu.rs
+    `SocialForceModelGpu`), running on one B200."""
+
+    def __init__(self, options, scenario, field, *, device: int = 0, math_mode: int = _capi.PEDONI_MATH_STRICT,
+                 capacity: int = 0, slab_rank: int = 0, slab_count: int = 1, stream: int = 0):
+        """`PedestrianModel::new(&SimulatorOptions, &Scenario, &Field)` (mod.rs:14)."""
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        dist = _f32(field.distance_map)
+        pots = _f32(field.potential_maps)
+        fy, fx = dist.shape
+        assert pots.ndim == 3 and pots.shape[1:] == (fy, fx), "potential_maps must be (n_maps, fy, fx)"
+        obstacles = _f32([[*o.line[0], *o.line[1], o.width] for o in scenario.obstacles]).reshape(-1, 5)
+        cfg = _capi.PedoniConfig()
+        cfg.struct_size = C.sizeof(_capi.PedoniConfig)
+        cfg.device = device
+        cfg.field_size_x, cfg.field_size_y = float(scenario.field.size[0]), float(scenario.field.size[1])
+        cfg.neighbor_grid_unit = float(options.neighbor_grid_unit)
+        cfg.field_grid_unit = float(field.unit)
+        cfg.use_neighbor_grid = int(bool(options.use_neighbor_grid))
+        cfg.use_distance_map = int(bool(options.use_distance_map))
+        cfg.field_ny, cfg.field_nx = fy, fx
+        cfg.n_potential_maps = pots.shape[0]
+        cfg.n_obstacles = obstacles.shape[0]
+        cfg.distance_map = _fp(dist)
+        cfg.potential_maps = _fp(pots)
+        cfg.obstacles = _fp(obstacles) if obstacles.shape[0] else None
+        cfg.capacity = capacity
+        cfg.math_mode = math_mode
+        cfg.slab_rank, cfg.slab_count = slab_rank, slab_count
+        cfg.stream = stream or None
+        _capi.check(self._lib.pedoni_create(C.byref(cfg), C.byref(self._h)))
+        self.n_maps = pots.shape[0]
+
+    # -- trait methods ---------------------------------------------------------------------------
+    @classmethod
+    def new(cls, options, scenario, field, **kw) -> "SocialForceModelCuda":
+        return cls(options, scenario, field, **kw)
+
+    def spawn_pedestrians(self, field, new_pedestrians: Sequence[Pedestrian], desired_speeds=None) -> None:
+        """mod.rs:19 / sfm.rs:48-89: append, then rebuild the neighbor grid (despawn + reorder).
+
+        `desired_speeds` are the N(1.34, 0.26) draws of sfm.rs:54, made by the caller (the
+        Simulator's seeded stream) so that device code has no RNG."""
+        n = len(new_pedestrians)
+        if n:
+            pos = _f32([p.pos for p in new_pedestrians]).reshape(n, 2)
+            dest = np.ascontiguousarray([p.destination for p in new_pedestrians], dtype=np.uint32)
+            if desired_speeds is None:
+                raise ValueError("desired_speeds must accompany spawned pedestrians")
+            self.spawn_arrays(pos, dest, _f32(desired_speeds))
+        self.rebuild()
+
+    def update_states(self, scenario=None, field=None) -> None:
+        """mod.rs:21 / sfm.rs:91-255."""
+        _capi.check(self._lib.pedoni_step(self._h), self._h)
+
+    def list_pedestrians(self) -> list:
+        """mod.rs:23 / sfm.rs:257-265."""
+        pos, dest = self.download(vel=False, v0=False)[:2]
+        return [Pedestrian(pos=(float(p[0]), float(p[1])), destination=int(d)) for p, d in zip(pos, dest)]
+
+    def get_pedestrian_count(self) -> int:
+        """mod.rs:25 / sfm.rs:267-269."""
+        return _capi.check(self._lib.pedoni_count(self._h), self._h)
+
+    # -- array-level entry points (what the trait methods are made of) ----------------------------
+    def spawn_arrays(self, pos: np.ndarray, dest: np.ndarray, v0: np.ndarray) -> None:
+        pos, v0 = _f32(pos), _f32(v0)
+        dest = np.ascontiguousarray(dest, dtype=np.uint32)
+        n = dest.shape[0]
+        assert pos.size == 2 * n and v0.size == n
+        _capi.check(self._lib.pedoni_spawn(self._h, n, _fp(pos), _up(dest), _fp(v0)), self._h)
+
+    def rebuild(self) -> None:
+        _capi.check(self._lib.pedoni_rebuild(self._h), self._h)
+
+    def step(self) -> None:
+        _capi.check(self._lib.pedoni_step(self._h), self._h)
+
+    def upload_state(self, pos, dest, vel, v0) -> None:
+        pos, vel, v0 = _f32(pos), _f32(vel), _f32(v0)
+        dest = np.ascontiguousarray(dest, dtype=np.uint32)
+        n = dest.shape[0]
+        assert pos.size == 2 * n and vel.size == 2 * n and v0.size == n
+        _capi.check(self._lib.pedoni_upload_state(self._h, n, _fp(pos), _up(dest), _fp(vel), _fp(v0)), self._h)
+
+    def download(self, vel: bool = True, v0: bool = True, out=None):
+        """Returns (pos[n,2], dest[n], vel[n,2] | None, v0[n] | None) in the model's current order."""
+        n = self.get_pedestrian_count()
+        if out is None:
+            pos = np.empty((n, 2), np.float32)
+            dest = np.empty(n, np.uint32)
+            velo = np.empty((n, 2), np.float32) if vel else None
+            v0o = np.empty(n, np.float32) if v0 else None
+        else:
+            pos, dest, velo, v0o = out
+        n_out = C.c_uint32()
+        _capi.check(self._lib.pedoni_download(self._h, _fp(pos), _up(dest), _fp(velo), _fp(v0o), dest.shape[0],
+                                              C.byref(n_out)), self._h)
+        k = n_out.value
+        return pos[:k], dest[:k], (velo[:k] if velo is not None else None), (v0o[:k] if v0o is not None else None)
+
+    def grid_shape(self):
+        ny, nx = C.c_int32(), C.c_int32()
+        _capi.check(self._lib.pedoni_grid_shape(self._h, C.byref(ny), C.byref(nx)), self._h)
+        return ny.value, nx.value
+
+    def cell_table(self) -> np.ndarray:
+        """`neighbor_grid_indices` (sfm.rs:22) of the last rebuild."""
+        ny, nx = self.grid_shape()
+        buf = np.empty(ny * nx + 1, np.uint32)
+        n = C.c_uint32()
+        _capi.check(self._lib.pedoni_cell_table(self._h, _up(buf), buf.shape[0], C.byref(n)), self._h)
+        return buf[: n.value]
+
+    def synchronize(self) -> None:
+        _capi.check(self._lib.pedoni_synchronize(self._h), self._h)
+
+    # -- measurement ----------------------------------------------------------------------------
+    def profile_enable(self, on: bool = True) -> None:
+        _capi.check(self._lib.pedoni_profile_enable(self._h, int(on)), self._h)
+
+    def profile_reset(self) -> None:
+        _capi.check(self._lib.pedoni_profile_reset(self._h), self._h)
+
+    def profile_read(self) -> dict:
+        t = _capi.PedoniKernelTimes()
+        _capi.check(self._lib.pedoni_profile_read(self._h, C.byref(t)), self._h)
+        return {name: getattr(t, name) for name, _ in t._fields_}
+
+    def timer_begin(self) -> None:
+        _capi.check(self._lib.pedoni_timer_begin(self._h), self._h)
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        _capi.check(self._lib.pedoni_timer_end(self._h, C.byref(ms)), self._h)
+        return ms.value
+
+    # -- slabs ------------------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes) -> None:
+        assert len(unique_id) == _capi.PEDONI_COMM_ID_BYTES
+        buf = C.create_string_buffer(unique_id, _capi.PEDONI_COMM_ID_BYTES)
+        _capi.check(self._lib.pedoni_comm_init(self._h, buf), self._h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.pedoni_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id() -> bytes:
+    lib = _capi.load()
+    buf = C.create_string_buffer(_capi.PEDONI_COMM_ID_BYTES)
+    _capi.check(lib.pedoni_comm_unique_id(buf))
+    return buf.raw
+
+
+def slab_rows(ny: int, count: int, rank: int):
+    lib = _capi.load()
+    r0, r1 = C.c_int32(), C.c_int32()
+    _capi.check(lib.pedoni_slab_rows(ny, count, rank, C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value

@@ -1,0 +1,69 @@
+"""Shared builders for the parity tests (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+
+import oracle
+from pedoni_b200 import Field, Scenario, SimulatorOptions
+from pedoni_b200.scenario import FieldConfig, ObstacleConfig, WaypointConfig
+
+# Stated fp32 tolerances (SURVEY.md §8d / BASELINE.json north_star "within a stated fp32 tolerance"):
+TOL_POS_ABS = 1e-4   # metres, per-step positions over a horizon of <= 10 steps
+TOL_VEL_ABS = 1e-4   # m/s
+
+
+def scenario_of(size, obstacles=(), waypoints=()):
+    sc = Scenario(field=FieldConfig(size=tuple(map(float, size))))
+    for o in obstacles:
+        sc.obstacles.append(ObstacleConfig(line=((o[0], o[1]), (o[2], o[3])), width=o[4]))
+    for w in waypoints:
+        sc.waypoints.append(WaypointConfig(line=((w[0], w[1]), (w[2], w[3])), width=w[4]))
+    return sc
+
+
+def arrays_of(sc):
+    obs = np.array([[*o.line[0], *o.line[1], o.width] for o in sc.obstacles], np.float32).reshape(-1, 5)
+    wps = np.array([[*w.line[0], *w.line[1], w.width] for w in sc.waypoints], np.float32).reshape(-1, 5)
+    return obs, wps
+
+
+def oracle_field(sc, unit=0.25) -> Field:
+    obs, wps = arrays_of(sc)
+    exist, dist, pots = oracle.field_build(sc.field.size, unit, obs, wps)
+    return Field(unit=unit, shape=dist.shape, obstacle_exist=exist, distance_map=dist, potential_maps=pots)
+
+
+def corridor_scenario(size=(60.0, 30.0)):
+    """Two facing waypoint lines and two long walls: a lanes.toml-like counter-flow corridor."""
+    w, h = size
+    return scenario_of(size,
+                       obstacles=[(0, 3.0, w, 3.0, 0.5), (0, h - 3.0, w, h - 3.0, 0.5), (w / 2, 10.0, w / 2, 14.0, 1.0)],
+                       waypoints=[(4.0, 5.0, 4.0, h - 5.0, 1.0), (w - 4.0, 5.0, w - 4.0, h - 5.0, 1.0)])
+
+
+def random_crowd(n, size, seed, n_dest=2, margin=2.0, speed=True):
+    rng = np.random.default_rng(seed)
+    pos = np.stack([rng.uniform(margin, size[0] - margin, n), rng.uniform(margin, size[1] - margin, n)], 1)
+    pos = pos.astype(np.float32)
+    dest = rng.integers(0, n_dest, n).astype(np.uint32)
+    v0 = np.clip(rng.normal(1.34, 0.26, n), 0.5, 2.2).astype(np.float32)
+    vel = (rng.normal(0, 0.5, (n, 2)) if speed else np.zeros((n, 2))).astype(np.float32)
+    return pos, dest, vel, v0
+
+
+def make_pair(sc, field, options=None, math_mode=0, **kw):
+    """(cuda model, oracle model) over the same scenario + field arrays."""
+    from pedoni_b200 import SocialForceModelCuda
+    options = options or SimulatorOptions()
+    obs, _ = arrays_of(sc)
+    cu = SocialForceModelCuda(options, sc, field, math_mode=math_mode, **kw)
+    orc = oracle.OracleModel(sc.field.size, options.neighbor_grid_unit, field.unit, field.distance_map,
+                             field.potential_maps, obstacles=obs, use_neighbor_grid=options.use_neighbor_grid,
+                             use_distance_map=options.use_distance_map)
+    return cu, orc
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)

@@ -1,0 +1,153 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded
+inputs. Bit-exact for cell keys / cell table / membership / order; stated fp32 tolerance for
+positions and velocities (helpers.TOL_*)."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import TOL_POS_ABS, TOL_VEL_ABS, bits
+from pedoni_b200 import PEDONI_MATH_FAST, PEDONI_MATH_STRICT, SimulatorOptions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def corridor():
+    sc = helpers.corridor_scenario()
+    return sc, helpers.oracle_field(sc)
+
+
+def _spawn_both(cu, orc, pos, dest, v0):
+    cu.spawn_arrays(pos, dest, v0)
+    cu.rebuild()
+    orc.spawn(pos, dest, v0)
+
+
+def _assert_rebuild_bit_exact(cu, orc):
+    assert cu.get_pedestrian_count() == orc.count()
+    np.testing.assert_array_equal(cu.cell_table(), orc.indices())
+    cp, cd, cv, c0 = cu.download()
+    op, od, ov, o0 = orc.get()
+    np.testing.assert_array_equal(bits(cp), bits(op))  # same agents, same (stable) order
+    np.testing.assert_array_equal(cd, od)
+    np.testing.assert_array_equal(bits(cv), bits(ov))
+    np.testing.assert_array_equal(bits(c0), bits(o0))
+
+
+def test_rebuild_bit_exact_with_drops_and_despawns(corridor):
+    sc, field = corridor
+    cu, orc = helpers.make_pair(sc, field)
+    pos, dest, vel, v0 = helpers.random_crowd(5000, sc.field.size, seed=1, margin=-3.0)  # some outside the grid
+    pos[:50] = np.array(sc.waypoints[0].line[0], np.float32) + np.random.default_rng(2).normal(0, 0.3, (50, 2)).astype(np.float32)
+    dest[:50] = 0  # standing on their destination: potential <= 0.25 -> despawn (sfm.rs:69)
+    pos[50] = (np.nan, 1.0)  # NaN -> cell (0, 0), predicate false -> dropped
+    _spawn_both(cu, orc, pos, dest, v0)
+    assert orc.count() < 5000
+    _assert_rebuild_bit_exact(cu, orc)
+
+
+@pytest.mark.parametrize("mode,tol_scale", [(PEDONI_MATH_STRICT, 1.0), (PEDONI_MATH_FAST, 1.0)])
+def test_ten_steps_within_tolerance(corridor, mode, tol_scale):
+    sc, field = corridor
+    cu, orc = helpers.make_pair(sc, field, math_mode=mode)
+    pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=3, margin=4.0)
+    cu.upload_state(pos, dest, vel, v0)
+    cu.rebuild()
+    orc.spawn(pos, dest, v0)
+    # give the oracle the same non-zero velocities (spawn sets them to zero): re-sort is identity afterwards
+    op, od, _, o0 = orc.get()
+    # map velocities through the same permutation: positions are unique, match on bits
+    order = {tuple(b): i for i, b in enumerate(bits(pos).tolist())}
+    perm = np.array([order[tuple(b)] for b in bits(op).tolist()])
+    orc.set(op, od, vel[perm], o0)
+    worst_p = worst_v = 0.0
+    for step in range(10):
+        cu.rebuild() if step else None
+        orc.spawn()
+        _assert_counts_and_table(cu, orc)
+        cu.step()
+        orc.update()
+        cp, cd, cv, _ = cu.download()
+        op, od, ov, _ = orc.get()
+        assert cp.shape == op.shape
+        worst_p = max(worst_p, float(np.nanmax(np.abs(cp - op))))
+        worst_v = max(worst_v, float(np.nanmax(np.abs(cv - ov))))
+        np.testing.assert_array_equal(np.isnan(cp), np.isnan(op))
+    print(f"mode={mode} worst |dpos|={worst_p:.3e} worst |dvel|={worst_v:.3e}")
+    assert worst_p <= TOL_POS_ABS * tol_scale and worst_v <= TOL_VEL_ABS * tol_scale
+
+
+def _assert_counts_and_table(cu, orc):
+    assert cu.get_pedestrian_count() == orc.count()
+    np.testing.assert_array_equal(cu.cell_table(), orc.indices())
+
+
+def test_strict_single_step_is_bit_exact_or_1ulp(corridor):
+    sc, field = corridor
+    cu, orc = helpers.make_pair(sc, field, math_mode=PEDONI_MATH_STRICT)
+    pos, dest, vel, v0 = helpers.random_crowd(4000, sc.field.size, seed=5, margin=4.0, speed=False)
+    _spawn_both(cu, orc, pos, dest, v0)
+    cu.step()
+    orc.update()
+    cp, _, cv, _ = cu.download()
+    op, _, ov, _ = orc.get()
+    mism = int((bits(cp) != bits(op)).sum() + (bits(cv) != bits(ov)).sum())
+    print(f"strict: {mism} of {cp.size + cv.size} floats differ in bits; max |dpos| = {np.abs(cp - op).max():.3e}")
+    # exp is the only op not bit-identical to glibc by construction; allow a vanishing fraction
+    assert mism <= 0.001 * (cp.size + cv.size)
+    assert np.abs(cp - op).max() <= 1e-6 and np.abs(cv - ov).max() <= 1e-5
+
+
+def test_segment_walls_variant(corridor):
+    sc, field = corridor
+    opts = SimulatorOptions(use_distance_map=False)
+    cu, orc = helpers.make_pair(sc, field, options=opts)
+    pos, dest, vel, v0 = helpers.random_crowd(2000, sc.field.size, seed=7, margin=4.0, speed=False)
+    _spawn_both(cu, orc, pos, dest, v0)
+    for _ in range(5):
+        cu.step()
+        orc.update()
+        cu.rebuild()
+        orc.spawn()
+        assert cu.get_pedestrian_count() == orc.count()
+    cp, _, cv, _ = cu.download()
+    op, _, ov, _ = orc.get()
+    assert np.abs(cp - op).max() <= TOL_POS_ABS and np.abs(cv - ov).max() <= TOL_VEL_ABS
+
+
+def test_spawn_stream_over_ticks(corridor):
+    """lib.rs:64-100 tick order: spawn_pedestrians(new) then update_states, new agents every tick."""
+    sc, field = corridor
+    cu, orc = helpers.make_pair(sc, field)
+    rng = np.random.default_rng(11)
+    for tick in range(30):
+        n = int(rng.poisson(20))
+        pos = np.stack([np.full(n, 6.0), rng.uniform(6, 24, n)], 1).astype(np.float32)
+        dest = np.ones(n, np.uint32)
+        v0 = np.clip(rng.normal(1.34, 0.26, n), 0.5, 2.2).astype(np.float32)
+        cu.spawn_arrays(pos, dest, v0)
+        cu.rebuild()
+        orc.spawn(pos, dest, v0)
+        _assert_counts_and_table(cu, orc)
+        cu.step()
+        orc.update()
+    cp, cd, cv, _ = cu.download()
+    op, od, ov, _ = orc.get()
+    np.testing.assert_array_equal(cd, od)
+    assert np.abs(cp - op).max() <= TOL_POS_ABS
+
+
+def test_empty_model_and_errors(corridor):
+    sc, field = corridor
+    cu, orc = helpers.make_pair(sc, field)
+    cu.rebuild()
+    cu.step()
+    assert cu.get_pedestrian_count() == 0
+    assert (cu.cell_table() == 0).all()
+    from pedoni_b200 import PedoniError
+    pos, dest, vel, v0 = helpers.random_crowd(10, sc.field.size, seed=1)
+    cu.spawn_arrays(pos, dest, v0)
+    with pytest.raises(PedoniError):  # step with un-rebuilt spawns
+        cu.step()
+    with pytest.raises(PedoniError):  # O(N^2) path is not built
+        helpers.make_pair(sc, field, options=SimulatorOptions(use_neighbor_grid=False))
