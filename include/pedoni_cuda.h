@@ -162,6 +162,10 @@ int pedoni_profile_enable(PedoniModel* model, int32_t enable); /* per-kernel eve
 int pedoni_profile_reset(PedoniModel* model);
 int pedoni_profile_read(PedoniModel* model, PedoniKernelTimes* out); /* blocks */
 
+/* Totals since creation: kernels this library launched, and pedestrian-updates integrated
+ * (sum over pedoni_step calls of the live population; accumulated on the device). Blocks. */
+int pedoni_counters(PedoniModel* model, uint64_t* kernel_launches, uint64_t* pedestrian_updates);
+
 /* Bracket a region with two events on the handle's stream; end blocks and returns elapsed ms. */
 int pedoni_timer_begin(PedoniModel* model);
 int pedoni_timer_end(PedoniModel* model, float* elapsed_ms);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "pedoni_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "pedoni_profile_reset": (C.c_int, [C.c_void_p]),
     "pedoni_profile_read": (C.c_int, [C.c_void_p, C.POINTER(PedoniKernelTimes)]),
+    "pedoni_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pedoni_timer_begin": (C.c_int, [C.c_void_p]),
     "pedoni_timer_end": (C.c_int, [C.c_void_p, c_float_p]),
     "pedoni_slab_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -29,6 +29,7 @@ struct ForceParams {
     uint32_t* keys_out;          // next rebuild's keys, indexed key_base + (id - begin)
     uint32_t key_base;
     uint32_t* error_flag;
+    unsigned long long* updates_total;  // += live agents of this launch (thread 0 of block 0)
     const float* obstacle_edges;  // segment-wall variant only
     int n_obstacles;
 };
@@ -90,6 +91,10 @@ __global__ void __launch_bounds__(128) force_integrate_kernel(ForceParams p) {
     const uint32_t local = p.first + blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t id = begin + local;
     const bool in_launch = local < p.first + p.count_upper;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t lo = min(begin + p.first, end), hi = min(begin + p.first + p.count_upper, end);
+        atomicAdd(p.updates_total, static_cast<unsigned long long>(hi - lo));
+    }
     const bool live = in_launch && id < end;
     // Slots between the live population and the host's upper bound must not carry a stale key.
     if (in_launch && !live) p.keys_out[p.key_base + local] = kKeyDrop;

@@ -37,7 +37,7 @@ constexpr int kMaxSegments = 4;
 
 struct Segment {
     AgentArrays a;
-    const uint32_t* d_range;  // device: [begin, end) of live entries inside the arrays
+    const uint32_t* d_range;  // device: [begin, end) of live entries inside the arrays; nullptr = [0, upper)
     uint32_t upper;           // host-known upper bound of (end - begin)
 };
 
@@ -53,7 +53,12 @@ __device__ __forceinline__ bool locate(const SortInput& in, uint32_t t, int& s, 
 #pragma unroll
     for (int k = 1; k < kMaxSegments; ++k)
         if (k < in.nseg && t >= in.prefix[k]) s = k;
-    uint32_t begin = in.seg[s].d_range[0], end = in.seg[s].d_range[1];
+    // d_range == nullptr: the population is host-known, [0, upper) (appended spawns).
+    uint32_t begin = 0, end = in.seg[s].upper;
+    if (in.seg[s].d_range != nullptr) {
+        begin = in.seg[s].d_range[0];
+        end = in.seg[s].d_range[1];
+    }
     idx = begin + (t - in.prefix[s]);
     return idx < end;
 }

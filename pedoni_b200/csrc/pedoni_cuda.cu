@@ -73,6 +73,8 @@ struct PedoniModel {
     uint32_t* d_total = nullptr;
     uint32_t* d_cur_range = nullptr;  // [begin, end) of owned agents in buf[cur]
     uint32_t* d_error = nullptr;
+    unsigned long long* d_updates = nullptr;
+    uint64_t launches = 0;  // kernels launched by this handle
     uint32_t* h_pub = nullptr;      // pinned, mapped: [begin, end, error] published by the device
     uint32_t* h_pub_dev = nullptr;  // device alias of h_pub
 
@@ -302,6 +304,7 @@ SortInput make_sort_input(PedoniModel* m) {
 template <Math M, bool D>
 void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem) {
     force_integrate_kernel<M, D><<<blocks, 128, smem, m->stream>>>(p);
+    m->launches += 1;
 }
 
 void launch_force(PedoniModel* m, const ForceParams& p) {
@@ -476,6 +479,8 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     CREATE_TRY(cudaMalloc(&m->d_total, sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&m->d_cur_range, sizeof(uint32_t) * 2));
     CREATE_TRY(cudaMalloc(&m->d_error, sizeof(uint32_t)));
+    CREATE_TRY(cudaMalloc(&m->d_updates, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemsetAsync(m->d_updates, 0, sizeof(unsigned long long), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_cell_start, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_cur_range, 0, sizeof(uint32_t) * 2, m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
@@ -516,6 +521,7 @@ void pedoni_destroy(PedoniModel* m) {
     cudaFree(m->d_total);
     cudaFree(m->d_cur_range);
     cudaFree(m->d_error);
+    cudaFree(m->d_updates);
     cudaFree(m->d_distance);
     cudaFree(m->d_potential);
     cudaFree(m->d_edges);
@@ -592,13 +598,16 @@ int pedoni_rebuild(PedoniModel* m) {
             ScopedTimer t(m, kKey);
             key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field, m->d_keys,
                                                                    m->d_error, /*foreign_rows_drop=*/true);
+            m->launches += 1;
         }
     }
     {
         ScopedTimer t(m, kHistogram);
         CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
-        if (total > 0)
+        if (total > 0) {
             histogram_kernel<<<div_up(total, 256), 256, 0, s>>>(total, m->d_keys, m->d_cell_count, m->d_ticket);
+            m->launches += 1;
+        }
     }
     {
         ScopedTimer t(m, kScan);
@@ -606,21 +615,25 @@ int pedoni_rebuild(PedoniModel* m) {
         scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(m->d_tile_sums, m->n_tiles, m->d_total);
         scan_apply_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums,
                                                               m->d_cell_start);
+        m->launches += 3;
     }
     if (total > 0) {
         {
             ScopedTimer t(m, kScatter);
             scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(total, m->d_keys, m->d_ticket, m->d_cell_start, m->d_perm);
+            m->launches += 1;
         }
         {
             ScopedTimer t(m, kGather);
             gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_keys, m->d_cell_start, m->d_perm,
                                                             m->buf[m->cur ^ 1]);
+            m->launches += 1;
         }
     }
     publish_range_kernel<<<1, 1, 0, s>>>(m->d_cell_start, m->own_begin_cell, m->own_end_cell, m->d_cur_range,
                                          m->h_pub_dev);
     publish_error_kernel<<<1, 1, 0, s>>>(m->d_error, m->h_pub_dev + 2);
+    m->launches += 2;
     CUDA_TRY(m, cudaGetLastError());
 
     m->cur ^= 1;
@@ -652,6 +665,7 @@ int pedoni_step(PedoniModel* m) {
         p.keys_out = m->d_keys;
         p.key_base = 0;
         p.error_flag = m->d_error;
+        p.updates_total = m->d_updates;
         p.obstacle_edges = m->d_edges;
         p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
         ScopedTimer t(m, kForce, m->cur_upper);
@@ -775,6 +789,18 @@ int pedoni_profile_read(PedoniModel* m, PedoniKernelTimes* out) {
     out->force_launches = m->acc_launches[kForce];
     out->comm_launches = m->acc_launches[kComm];
     out->force_agents = m->acc_force_agents;
+    return PEDONI_OK;
+}
+int pedoni_counters(PedoniModel* m, uint64_t* kernel_launches, uint64_t* pedestrian_updates) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (kernel_launches) *kernel_launches = m->launches;
+    if (pedestrian_updates) {
+        unsigned long long v = 0;
+        CUDA_TRY(m, cudaMemcpyAsync(&v, m->d_updates, sizeof v, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+        *pedestrian_updates = v;
+    }
     return PEDONI_OK;
 }
 int pedoni_timer_begin(PedoniModel* m) {

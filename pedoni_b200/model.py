@@ -170,6 +170,12 @@ class SocialForceModelCuda:
         _capi.check(self._lib.pedoni_profile_read(self._h, C.byref(t)), self._h)
         return {name: getattr(t, name) for name, _ in t._fields_}
 
+    def counters(self):
+        """(kernel launches, pedestrian-updates) since creation."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _capi.check(self._lib.pedoni_counters(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
     def timer_begin(self) -> None:
         _capi.check(self._lib.pedoni_timer_begin(self._h), self._h)
 

@@ -46,8 +46,8 @@ def test_rebuild_bit_exact_with_drops_and_despawns(corridor):
     _assert_rebuild_bit_exact(cu, orc)
 
 
-@pytest.mark.parametrize("mode,tol_scale", [(PEDONI_MATH_STRICT, 1.0), (PEDONI_MATH_FAST, 1.0)])
-def test_ten_steps_within_tolerance(corridor, mode, tol_scale):
+@pytest.mark.parametrize("mode", [PEDONI_MATH_STRICT, PEDONI_MATH_FAST])
+def test_ten_steps_within_tolerance(corridor, mode):
     sc, field = corridor
     cu, orc = helpers.make_pair(sc, field, math_mode=mode)
     pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=3, margin=4.0)
@@ -74,7 +74,8 @@ def test_ten_steps_within_tolerance(corridor, mode, tol_scale):
         worst_v = max(worst_v, float(np.nanmax(np.abs(cv - ov))))
         np.testing.assert_array_equal(np.isnan(cp), np.isnan(op))
     print(f"mode={mode} worst |dpos|={worst_p:.3e} worst |dvel|={worst_v:.3e}")
-    assert worst_p <= TOL_POS_ABS * tol_scale and worst_v <= TOL_VEL_ABS * tol_scale
+    tol_p, tol_v = helpers.tolerances(mode)
+    assert worst_p <= tol_p and worst_v <= tol_v
 
 
 def _assert_counts_and_table(cu, orc):
