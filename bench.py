@@ -301,10 +301,11 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        force_ms = prof["force_ms"] / max(prof["force_launches"], 1)
-        agents_per_launch = prof["force_agents"] / max(prof["force_launches"], 1)
-        # force_agents counts the host's upper bound per launch; use the device-side live count instead
-        agents_per_launch = updates / max(prof["force_launches"], 1)
+        # One force launch per step on a whole-domain handle; a slab handle adds two small edge launches
+        # (ghost-adjacent rows) on its second stream. Quote per step: all force launches of one step
+        # and the agents they integrated (device-side live count, not the host's upper bound).
+        force_ms = prof["force_ms"] / args.steps
+        agents_per_launch = updates / args.steps
         achieved = ALGO_BYTES_PER_UPDATE * agents_per_launch / (force_ms * 1e-3) / 1e9
         step_kernel_ms = {k[:-3]: prof[k] / args.steps for k in prof if k.endswith("_ms")}
         out = {

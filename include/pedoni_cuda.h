@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PEDONI_ABI_VERSION 1
+#define PEDONI_ABI_VERSION 2
 
 typedef struct PedoniModel PedoniModel;
 
@@ -41,7 +41,7 @@ typedef enum PedoniStatus {
     PEDONI_OK = 0,
     PEDONI_ERR_INVALID = -1,     /* bad argument / config */
     PEDONI_ERR_CUDA = -2,        /* CUDA runtime or driver error (message has the CUDA string) */
-    PEDONI_ERR_STATE = -3,       /* call sequence error (e.g. step with un-rebuilt spawns) */
+    PEDONI_ERR_STATE = -3,       /* call sequence error (e.g. step without a fresh rebuild) */
     PEDONI_ERR_CAPACITY = -4,    /* caller buffer too small / device buffer overflow */
     PEDONI_ERR_UNSUPPORTED = -5, /* option the CUDA path does not implement (use_neighbor_grid = 0) */
     PEDONI_ERR_COMM = -6         /* NCCL failure (multi-GPU slabs) */
@@ -90,6 +90,11 @@ typedef struct PedoniConfig {
     int32_t slab_count;
 
     void* stream;                /* optional cudaStream_t to enqueue on (NULL: the handle owns one) */
+
+    /* Slab handles: capacity, in pedestrians, of one two-row ghost strip (= of one halo message).
+     * 0 = auto (4x the two-row population of a uniformly filled slab of `capacity` agents, >= 4096).
+     * All slabs of one decomposition must use the same value. */
+    uint32_t halo_capacity;
 } PedoniConfig;
 
 int pedoni_abi_version(void);
@@ -170,16 +175,36 @@ int pedoni_counters(PedoniModel* model, uint64_t* kernel_launches, uint64_t* ped
 int pedoni_timer_begin(PedoniModel* model);
 int pedoni_timer_end(PedoniModel* model, float* elapsed_ms);
 
-/* ---- multi-GPU slabs (one process per GPU; NCCL send/recv between slab neighbours) -------------- */
+/* ---- multi-GPU slabs (one handle per GPU; NCCL send/recv between slab neighbours) -----------------
+ *
+ * The neighbor grid is cut into `slab_count` bands of whole cell rows (pedoni_slab_rows). A slab handle
+ * owns the pedestrians whose cell row is in its band and additionally holds two GHOST rows each side,
+ * copies of its neighbours' boundary rows. Per tick it integrates its own rows plus the nearest ghost
+ * row each side (redundantly, bit-identically to the owner), so a pedestrian that walks across a band
+ * boundary is adopted by the receiving slab's own rebuild: halo strips and migrating pedestrians
+ * travel in the same message. After every pedoni_rebuild the handle sends its first/last two owned
+ * rows (24 B per pedestrian + the rows' cell table) to rank-1 / rank+1 on a second stream while
+ * pedoni_step's interior kernel runs; only the four rows next to a boundary wait for the exchange.
+ * Concatenating the ranks' pedoni_download outputs in rank order reproduces the whole-domain order.
+ */
 
 /* Rows [*row0, *row1) of the ny-row neighbor grid owned by `rank` of `count` slabs. Pure host. */
 int pedoni_slab_rows(int32_t ny, int32_t count, int32_t rank, int32_t* row0, int32_t* row1);
 
 #define PEDONI_COMM_ID_BYTES 128
 /* Rank 0 creates the NCCL unique id; the host program (torch.distributed, MPI, a socket) hands the
- * 128 bytes to every rank, which then joins with pedoni_comm_init. */
+ * 128 bytes to every rank, which then joins with pedoni_comm_init (collective over the slab ranks). */
 int pedoni_comm_unique_id(void* out_id128);
 int pedoni_comm_init(PedoniModel* model, const void* id128);
+
+/* In-process transport for slabs that live in ONE process (several handles on one GPU, or one per GPU
+ * under one host thread): after pedoni_rebuild has been called on every handle, exchange their ghost
+ * rows with device-to-device copies. models[i] must be slab i of n. Used where NCCL cannot be (tests
+ * of the slab path on a single GPU); handles joined with pedoni_comm_init exchange by themselves. */
+int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n);
+
+/* The halo capacity in effect (0 on a whole-domain handle). */
+int pedoni_halo_capacity(const PedoniModel* model, uint32_t* halo_capacity);
 
 #ifdef __cplusplus
 }

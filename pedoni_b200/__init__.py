@@ -5,7 +5,7 @@ reference's `PedestrianModel` plugin trait, through the C ABI in include/pedoni_
 The product is libpedoni_cuda.so (hand-written sm_100a CUDA + a C++ host layer); this Python package
 is the ctypes harness the tests and bench.py drive it with. There is no CPU fallback.
 """
-from .model import Pedestrian, SocialForceModelCuda, comm_unique_id, slab_rows  # noqa: F401
+from .model import Pedestrian, SlabGroup, SocialForceModelCuda, comm_unique_id, slab_rows  # noqa: F401
 from .options import Backend, SimulatorOptions  # noqa: F401
 from .scenario import Scenario  # noqa: F401
 from .field import Field  # noqa: F401

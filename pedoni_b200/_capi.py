@@ -12,7 +12,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libpedoni_cuda.so"
 
-PEDONI_ABI_VERSION = 1
+PEDONI_ABI_VERSION = 2
 PEDONI_OK = 0
 PEDONI_ERR_INVALID = -1
 PEDONI_ERR_CUDA = -2
@@ -50,6 +50,7 @@ class PedoniConfig(C.Structure):
         ("slab_rank", C.c_int32),
         ("slab_count", C.c_int32),
         ("stream", C.c_void_p),
+        ("halo_capacity", C.c_uint32),
     ]
 
 
@@ -85,6 +86,8 @@ SIGNATURES = {
     "pedoni_slab_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pedoni_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pedoni_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pedoni_slab_exchange_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32]),
+    "pedoni_halo_capacity": (C.c_int, [C.c_void_p, c_u32_p]),
 }
 
 _lib = None

@@ -21,15 +21,14 @@ struct ForceParams {
     AgentArrays in;              // cell-sorted state (pre-integration)
     AgentArrays out;             // integrated state, same indexing
     const uint32_t* d_range;     // device [begin, end): agents this launch integrates
-    uint32_t first;              // launch covers begin + first + [0, count_upper)
-    uint32_t count_upper;
+    const uint32_t* d_owned;     // device [begin, end): agents this handle owns (the updates counter counts these)
+    uint32_t count_upper;        // host upper bound of end - begin (grid size)
     const uint32_t* cell_start;  // local cell table (neighbor_grid_indices, sfm.rs:22)
     GridView grid;
     FieldView field;
-    uint32_t* keys_out;          // next rebuild's keys, indexed key_base + (id - begin)
-    uint32_t key_base;
+    uint32_t* keys_out;          // next rebuild's keys, indexed like the arrays
     uint32_t* error_flag;
-    unsigned long long* updates_total;  // += live agents of this launch (thread 0 of block 0)
+    unsigned long long* updates_total;  // += owned agents of this launch (thread 0 of block 0)
     const float* obstacle_edges;  // segment-wall variant only
     int n_obstacles;
 };
@@ -88,21 +87,18 @@ __global__ void __launch_bounds__(128) force_integrate_kernel(ForceParams p) {
     extern __shared__ float s_edges[];
 
     const uint32_t begin = p.d_range[0], end = p.d_range[1];
-    const uint32_t local = p.first + blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t id = begin + local;
-    const bool in_launch = local < p.first + p.count_upper;
+    const uint32_t id = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const uint32_t lo = min(begin + p.first, end), hi = min(begin + p.first + p.count_upper, end);
-        atomicAdd(p.updates_total, static_cast<unsigned long long>(hi - lo));
+        const uint32_t lo = max(begin, p.d_owned[0]), hi = min(end, p.d_owned[1]);
+        if (hi > lo) atomicAdd(p.updates_total, static_cast<unsigned long long>(hi - lo));
     }
-    const bool live = in_launch && id < end;
-    // Slots between the live population and the host's upper bound must not carry a stale key.
-    if (in_launch && !live) p.keys_out[p.key_base + local] = kKeyDrop;
+    const bool live = id < end;
     if (kDistanceMap && !live) return;  // the segment variant needs every thread at its barriers
 
     float2 pos = make_float2(0.f, 0.f), vel = pos, e = pos, acc = pos;
     float v0 = 0.f;
     uint32_t dest = 0;
+    int row = 0;
     if (live) {
         pos = p.in.pos[id];
         vel = p.in.vel[id];
@@ -125,6 +121,7 @@ __global__ void __launch_bounds__(128) force_integrate_kernel(ForceParams p) {
         // ---- pair repulsion (sfm.rs:112-156)
         {
             const int2 c = cell_of(pos, p.grid.unit);
+            row = c.y;
             // Reference clamps to the grid; the local table may start at row_base (slabs) and always
             // holds every row a live agent can reach (its own rows plus one halo row each side).
             const int ly = c.y - p.grid.row_base;
@@ -209,7 +206,13 @@ __global__ void __launch_bounds__(128) force_integrate_kernel(ForceParams p) {
     p.out.vel[id] = vn;
     p.out.v0[id] = v0;
     p.out.dest[id] = dest;
-    p.keys_out[p.key_base + local] = sort_key(p.grid, p.field, pn, dest, p.error_flag);
+    p.keys_out[id] = sort_key(p.grid, p.field, pn, dest, p.error_flag);
+    // Slab handles exchange two ghost rows per tick, which covers every move of less than one grid row
+    // (1.4 m per 0.1 s); anything faster would silently vanish at a slab boundary, so flag it.
+    if (p.grid.slab) {
+        const int new_row = __float2int_rz(S::div(pn.y, p.grid.unit));
+        if (abs(new_row - row) >= 2 && pn.y == pn.y) atomicOr(p.error_flag, kErrRowJump);
+    }
 }
 
 }  // namespace pedoni

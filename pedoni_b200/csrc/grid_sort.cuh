@@ -1,4 +1,5 @@
-// grid_sort.cuh — neighbor-grid rebuild as a deterministic, stable cell-key counting sort (sm_100a).
+// grid_sort.cuh — neighbor-grid rebuild as a deterministic, stable cell-key counting sort (sm_100a),
+// plus the ghost-row pack/unpack of the slab decomposition.
 //
 // Replaces NeighborGrid::update (neighbor_grid.rs:22-36) and the serial walk/gather of
 // SocialForceModel::spawn_pedestrians (sfm.rs:58-77):
@@ -16,11 +17,19 @@
 //              arrival order, i.e. run-to-run deterministic. Then one coalesced read / near-coalesced
 //              write of the 24-byte state into the other buffer.
 //
-// The sort input is a virtual concatenation of up to kMaxSegments segments (inbound migrants from
-// the slab below, the resident agents, inbound migrants from above, appended spawns): the order of
-// the concatenation is the order of "previous index", which for slabs reproduces the single-GPU
-// order exactly. Segment populations live in device memory so no host synchronisation is needed
+// The sort input is a virtual concatenation of segments (the resident agents this handle just
+// integrated — its owned rows plus, on a slab handle, one ghost row each side — then the appended
+// spawns): the order of the concatenation is the order of "previous index", which for slabs
+// reproduces the single-GPU order exactly because ghost rows sit in the array where their rows sit in
+// the global order. Segment populations live in device memory so no host synchronisation is needed
 // between ticks; grids are sized from host-known upper bounds.
+//
+// Array layout of a slab handle (H = halo capacity), all four SoA columns alike:
+//   [H - n_below, H)                      ghost rows r0-2, r0-1 (copied from the slab below)
+//   [H, H + n_owned)                      owned rows r0 .. r1-1, cell-sorted
+//   [H + n_owned, H + n_owned + n_above)  ghost rows r1, r1+1 (copied from the slab above)
+// so the local cell table indexes one contiguous run and keeps the reference's (cells + 1) layout.
+// A whole-domain handle is the same with H = 0 and no ghosts.
 #pragma once
 #include "sfm_device.cuh"
 
@@ -33,10 +42,21 @@ struct AgentArrays {
     uint32_t* dest;  // sfm.rs:29 destination
 };
 
-constexpr int kMaxSegments = 4;
+// Device-resident [begin, end) pairs describing the current layout (PedoniModel::d_ranges).
+enum RangeId : int {
+    kRangeOwned = 0,     // agents this handle owns (what count / download report)
+    kRangeCompute = 1,   // agents this handle integrates: owned + one ghost row each side
+    kRangeInterior = 2,  // owned agents whose 3x3 block touches no ghost row
+    kRangeEdgeLo = 3,    // ghost row r0-1 + owned row r0 (needs the halo from below)
+    kRangeEdgeHi = 4,    // owned row r1-1 + ghost row r1 (needs the halo from above)
+    kNumRanges = 5
+};
+
+constexpr int kMaxSegments = 2;
 
 struct Segment {
     AgentArrays a;
+    uint32_t* keys;           // sort keys, indexed like the arrays
     const uint32_t* d_range;  // device: [begin, end) of live entries inside the arrays; nullptr = [0, upper)
     uint32_t upper;           // host-known upper bound of (end - begin)
 };
@@ -47,47 +67,62 @@ struct SortInput {
     int nseg;
 };
 
-// Logical input index t -> (segment, element index) or false if t is beyond the segment's live range.
-__device__ __forceinline__ bool locate(const SortInput& in, uint32_t t, int& s, uint32_t& idx) {
-    s = 0;
-#pragma unroll
-    for (int k = 1; k < kMaxSegments; ++k)
-        if (k < in.nseg && t >= in.prefix[k]) s = k;
+// Logical input index t -> the segment's arrays and the element index; live = false if t is beyond the
+// segment's live range. Two segments, resolved with selects (no dynamic indexing of the kernel
+// parameter, which would force a local-memory copy).
+struct Located {
+    AgentArrays a;
+    uint32_t* keys;
+    uint32_t idx;
+    bool live;
+};
+static_assert(kMaxSegments == 2, "locate() selects between exactly two segments");
+
+__device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
+    const bool second = in.nseg > 1 && t >= in.prefix[1];
+    Located r;
+    r.a.pos = second ? in.seg[1].a.pos : in.seg[0].a.pos;
+    r.a.vel = second ? in.seg[1].a.vel : in.seg[0].a.vel;
+    r.a.v0 = second ? in.seg[1].a.v0 : in.seg[0].a.v0;
+    r.a.dest = second ? in.seg[1].a.dest : in.seg[0].a.dest;
+    r.keys = second ? in.seg[1].keys : in.seg[0].keys;
+    const uint32_t* d_range = second ? in.seg[1].d_range : in.seg[0].d_range;
     // d_range == nullptr: the population is host-known, [0, upper) (appended spawns).
-    uint32_t begin = 0, end = in.seg[s].upper;
-    if (in.seg[s].d_range != nullptr) {
-        begin = in.seg[s].d_range[0];
-        end = in.seg[s].d_range[1];
+    uint32_t begin = 0, end = second ? in.seg[1].upper : in.seg[0].upper;
+    if (d_range != nullptr) {
+        begin = d_range[0];
+        end = d_range[1];
     }
-    idx = begin + (t - in.prefix[s]);
-    return idx < end;
+    r.idx = begin + (t - (second ? in.prefix[1] : in.prefix[0]));
+    r.live = r.idx < end;
+    return r;
 }
 
 // ---- key: only for logical indices in [t_begin, t_end) whose keys are not fresh -------------------
 __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin, uint32_t t_end, GridView g,
-                                                  FieldView f, uint32_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ error_flag, bool foreign_rows_drop) {
+                                                  FieldView f, uint32_t* __restrict__ error_flag) {
     uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
-    int s;
-    uint32_t idx;
-    uint32_t key = kKeyDrop;
-    if (locate(in, t, s, idx)) {
-        key = sort_key(g, f, in.seg[s].a.pos[idx], in.seg[s].a.dest[idx], error_flag);
-        // Spawn lists are replicated to every slab; the owner keeps the agent, everybody else drops it.
-        if (foreign_rows_drop && (key == kKeyMigrateDown || key == kKeyMigrateUp)) key = kKeyDrop;
-    }
-    keys[t] = key;
+    const Located l = locate(in, t);
+    if (!l.live) return;
+    // Spawn lists are replicated to every slab and ghost rows are copies: sort_key keeps an agent only
+    // on the handle that owns its row.
+    l.keys[l.idx] = sort_key(g, f, l.a.pos[l.idx], l.a.dest[l.idx], error_flag);
 }
 
 // ---- histogram -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) histogram_kernel(uint32_t total_upper, const uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) histogram_kernel(SortInput in, uint32_t total_upper,
                                                         uint32_t* __restrict__ cell_count,
                                                         uint32_t* __restrict__ ticket) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_upper) return;
-    uint32_t key = keys[t];
-    if (key < kKeyFirstSpecial) ticket[t] = atomicAdd(cell_count + key, 1u);
+    uint32_t tk = kKeyDrop;  // ticket[t] == kKeyDrop <=> logical index t is not kept
+    const Located l = locate(in, t);
+    if (l.live) {
+        uint32_t key = l.keys[l.idx];
+        if (key < kKeyFirstSpecial) tk = atomicAdd(cell_count + key, 1u);
+    }
+    ticket[t] = tk;
 }
 
 // ---- scan: exclusive prefix over n_cells counters, three launches built from block-wide scans -----
@@ -141,9 +176,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// Single block: exclusive scan of the tile sums in place; writes the grand total.
-__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(uint32_t* __restrict__ tile_sums, uint32_t n_tiles,
-                                                                  uint32_t* __restrict__ d_total) {
+// Single block: exclusive scan of the tile sums in place.
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(uint32_t* __restrict__ tile_sums, uint32_t n_tiles) {
     __shared__ uint32_t total;
     uint32_t carry = 0;
     for (uint32_t base = 0; base < n_tiles; base += kScanThreads) {
@@ -154,13 +188,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(uint32_t* __re
         carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *d_total = carry;
 }
 
-// cell_start[c] = exclusive prefix; cell_start[n_cells] = total.
+// cell_start[c] = offset + exclusive prefix; cell_start[n_cells] = offset + total. `offset` is the
+// halo capacity H on a slab handle (owned agents start at H), 0 otherwise.
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ cell_count,
                                                                   uint32_t n_cells,
                                                                   const uint32_t* __restrict__ tile_sums,
+                                                                  uint32_t offset,
                                                                   uint32_t* __restrict__ cell_start) {
     __shared__ uint32_t total;
     const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -171,7 +206,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
         v[k] = (base + k < n_cells) ? cell_count[base + k] : 0u;
         sum += v[k];
     }
-    uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan(sum, &total);
+    uint32_t run = offset + tile_sums[blockIdx.x] + block_exclusive_scan(sum, &total);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         if (base + k < n_cells) cell_start[base + k] = run;
@@ -181,49 +216,166 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 }
 
 // ---- scatter: perm[start[cell] + ticket] = t -----------------------------------------------------
-__global__ void __launch_bounds__(256) scatter_kernel(uint32_t total_upper, const uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) scatter_kernel(SortInput in, uint32_t total_upper,
                                                       const uint32_t* __restrict__ ticket,
                                                       const uint32_t* __restrict__ cell_start,
                                                       uint32_t* __restrict__ perm) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_upper) return;
-    uint32_t key = keys[t];
-    if (key < kKeyFirstSpecial) perm[__ldg(cell_start + key) + ticket[t]] = t;
+    const uint32_t tk = ticket[t];
+    if (tk == kKeyDrop) return;
+    const Located l = locate(in, t);
+    perm[__ldg(cell_start + l.keys[l.idx]) + tk] = t;
 }
 
 // ---- gather: stable rank inside the cell, then move the 24-byte state ----------------------------
 __global__ void __launch_bounds__(256) gather_kernel(SortInput in, uint32_t total_upper,
-                                                     const uint32_t* __restrict__ keys,
+                                                     const uint32_t* __restrict__ ticket,
                                                      const uint32_t* __restrict__ cell_start,
                                                      const uint32_t* __restrict__ perm, AgentArrays out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_upper) return;
-    uint32_t key = keys[t];
-    if (key >= kKeyFirstSpecial) return;
-    int s;
-    uint32_t idx;
-    locate(in, t, s, idx);  // live by construction: dead logical indices carry kKeyDrop
+    if (ticket[t] == kKeyDrop) return;
+    const Located l = locate(in, t);
+    const uint32_t idx = l.idx;
+    const uint32_t key = l.keys[idx];
     const uint32_t begin = __ldg(cell_start + key), end = __ldg(cell_start + key + 1);
     uint32_t rank = 0;
     for (uint32_t j = begin; j < end; ++j) rank += (__ldg(perm + j) < t) ? 1u : 0u;
     const uint32_t dst = begin + rank;
-    const AgentArrays& a = in.seg[s].a;
+    const AgentArrays& a = l.a;
     out.pos[dst] = a.pos[idx];
     out.vel[dst] = a.vel[idx];
     out.v0[dst] = a.v0[idx];
     out.dest[dst] = a.dest[idx];
 }
 
-// Publishes [begin, end) of the agents this handle owns after a rebuild, to the device-side range the
-// next kernels read and to a pinned host slot (read by pedoni_count / pedoni_download after a sync).
-__global__ void publish_range_kernel(const uint32_t* __restrict__ cell_start, uint32_t own_begin_cell,
-                                     uint32_t own_end_cell, uint32_t* __restrict__ d_range,
-                                     uint32_t* __restrict__ host_slot) {
-    uint32_t b = cell_start[own_begin_cell], e = cell_start[own_end_cell];
-    d_range[0] = b;
-    d_range[1] = e;
-    host_slot[0] = b;
-    host_slot[1] = e;
+// ---- layout ranges --------------------------------------------------------------------------------
+// After the scan: the ranges that depend on the owned rows only, and the owned count for the host
+// (one aligned 64-bit store to pinned memory: tick << 32 | n_owned, so a lagging reader never sees a
+// torn pair). On a handle without ghosts this also fixes the compute / edge ranges.
+__global__ void publish_layout_kernel(const uint32_t* __restrict__ cell_start, uint32_t own_begin_cell,
+                                      uint32_t own_end_cell, uint32_t nx, int has_below, int has_above,
+                                      uint32_t* __restrict__ ranges, unsigned long long* __restrict__ host_slot,
+                                      uint32_t tick) {
+    const uint32_t b = cell_start[own_begin_cell], e = cell_start[own_end_cell];
+    ranges[2 * kRangeOwned] = b;
+    ranges[2 * kRangeOwned + 1] = e;
+    ranges[2 * kRangeInterior] = has_below ? cell_start[own_begin_cell + nx] : b;
+    ranges[2 * kRangeInterior + 1] = has_above ? cell_start[own_end_cell - nx] : e;
+    if (!has_below) {
+        ranges[2 * kRangeCompute] = b;
+        ranges[2 * kRangeEdgeLo] = b;
+        ranges[2 * kRangeEdgeLo + 1] = b;
+    }
+    if (!has_above) {
+        ranges[2 * kRangeCompute + 1] = e;
+        ranges[2 * kRangeEdgeHi] = e;
+        ranges[2 * kRangeEdgeHi + 1] = e;
+    }
+    *host_slot = (static_cast<unsigned long long>(tick) << 32) | static_cast<unsigned long long>(e - b);
+}
+
+// ---- ghost rows -----------------------------------------------------------------------------------
+// One message per direction, a flat array of 32-bit words:
+//   [0] n = agents in the two rows   [1] tick   [2 .. 2 + 2nx] starts relative to the first agent
+//   then pos (2H words), vel (2H), desired_speed (H), destination (H), H = halo capacity.
+__host__ __device__ inline uint32_t halo_header_words(uint32_t nx) { return (2u * nx + 3u + 3u) & ~3u; }
+__host__ __device__ inline size_t halo_message_words(uint32_t nx, uint32_t halo_cap) {
+    return static_cast<size_t>(halo_header_words(nx)) + 6ull * halo_cap;
+}
+
+struct HaloMessage {
+    uint32_t* words;
+    __host__ __device__ uint32_t* starts() const { return words + 2; }
+    __host__ __device__ float2* pos(uint32_t nx, uint32_t) const {
+        return reinterpret_cast<float2*>(words + halo_header_words(nx));
+    }
+    __host__ __device__ float2* vel(uint32_t nx, uint32_t h) const {
+        return reinterpret_cast<float2*>(words + halo_header_words(nx) + 2ull * h);
+    }
+    __host__ __device__ float* v0(uint32_t nx, uint32_t h) const {
+        return reinterpret_cast<float*>(words + halo_header_words(nx) + 4ull * h);
+    }
+    __host__ __device__ uint32_t* dest(uint32_t nx, uint32_t h) const { return words + halo_header_words(nx) + 5ull * h; }
+};
+
+// blockIdx.y = 0: the first two owned rows -> message for the slab below;
+// blockIdx.y = 1: the last two owned rows  -> message for the slab above.
+__global__ void __launch_bounds__(256) halo_pack_kernel(AgentArrays a, const uint32_t* __restrict__ cell_start,
+                                                        uint32_t own_begin_cell, uint32_t own_end_cell, uint32_t nx,
+                                                        uint32_t halo_cap, HaloMessage down, HaloMessage up,
+                                                        int has_below, int has_above, uint32_t tick,
+                                                        uint32_t* __restrict__ error_flag) {
+    const int side = blockIdx.y;
+    if ((side == 0 && !has_below) || (side == 1 && !has_above)) return;
+    const HaloMessage msg = side == 0 ? down : up;
+    const uint32_t c0 = side == 0 ? own_begin_cell : own_end_cell - 2 * nx;
+    const uint32_t first = cell_start[c0];
+    uint32_t n = cell_start[c0 + 2 * nx] - first;
+    const bool overflow = n > halo_cap;
+    if (overflow) n = 0;  // ship nothing rather than a torn strip; the flag surfaces at the next blocking call
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        msg.words[0] = n;
+        msg.words[1] = tick;
+        if (overflow) atomicOr(error_flag, kErrHaloOverflow);
+    }
+    if (i <= 2 * nx) msg.starts()[i] = overflow ? 0u : cell_start[c0 + i] - first;
+    if (i < n) {
+        msg.pos(nx, halo_cap)[i] = a.pos[first + i];
+        msg.vel(nx, halo_cap)[i] = a.vel[first + i];
+        msg.v0(nx, halo_cap)[i] = a.v0[first + i];
+        msg.dest(nx, halo_cap)[i] = a.dest[first + i];
+    }
+}
+
+// blockIdx.y = 0: ghost rows r0-2, r0-1 from `below` (right-aligned to end at H);
+// blockIdx.y = 1: ghost rows r1, r1+1 from `above` (placed right after the owned agents).
+// Also completes the cell table for the ghost rows and the compute / edge ranges.
+__global__ void __launch_bounds__(256) halo_unpack_kernel(AgentArrays a, uint32_t* __restrict__ cell_start,
+                                                          uint32_t own_begin_cell, uint32_t own_end_cell, uint32_t nx,
+                                                          uint32_t halo_cap, uint32_t array_cap, HaloMessage below,
+                                                          HaloMessage above, int has_below, int has_above,
+                                                          uint32_t* __restrict__ ranges,
+                                                          uint32_t* __restrict__ error_flag) {
+    const int side = blockIdx.y;
+    if ((side == 0 && !has_below) || (side == 1 && !has_above)) return;
+    const HaloMessage msg = side == 0 ? below : above;
+    uint32_t n = msg.words[0];
+    if (n > halo_cap) n = 0;  // cannot happen with a matching sender; never index out of bounds
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* rel = msg.starts();
+    uint32_t base;
+    if (side == 0) {
+        base = halo_cap - n;
+        if (i < 2 * nx) cell_start[i] = base + min(rel[i], n);  // entry 2nx == own_begin_cell == H already
+        if (i == 0) {
+            const uint32_t row_m1 = base + min(rel[nx], n);  // first agent of ghost row r0-1
+            ranges[2 * kRangeCompute] = row_m1;
+            ranges[2 * kRangeEdgeLo] = row_m1;
+            ranges[2 * kRangeEdgeLo + 1] = cell_start[own_begin_cell + nx];
+        }
+    } else {
+        base = cell_start[own_end_cell];  // H + n_owned, written by the scan
+        if (base + n > array_cap) {       // host sizing bug or a burst of immigrants; drop the strip, flag it
+            if (i == 0) atomicOr(error_flag, kErrHaloOverflow);
+            n = 0;
+        }
+        if (i >= 1 && i <= 2 * nx) cell_start[own_end_cell + i] = base + min(rel[i], n);
+        if (i == 0) {
+            const uint32_t row_p1 = base + min(rel[nx], n);  // one past the last agent of ghost row r1
+            ranges[2 * kRangeCompute + 1] = row_p1;
+            ranges[2 * kRangeEdgeHi] = cell_start[own_end_cell - nx];
+            ranges[2 * kRangeEdgeHi + 1] = row_p1;
+        }
+    }
+    if (i < n) {
+        a.pos[base + i] = msg.pos(nx, halo_cap)[i];
+        a.vel[base + i] = msg.vel(nx, halo_cap)[i];
+        a.v0[base + i] = msg.v0(nx, halo_cap)[i];
+        a.dest[base + i] = msg.dest(nx, halo_cap)[i];
+    }
 }
 
 }  // namespace pedoni

@@ -41,7 +41,8 @@ struct TimedLaunch {
 
 struct PedoniModel {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // main: rebuild, interior force
+    cudaStream_t edge_stream = nullptr;  // slab handles: halo exchange, ghost unpack, edge force
     bool own_stream = false;
     int math_mode = 0;
     bool use_distance_map = true;
@@ -55,14 +56,30 @@ struct PedoniModel {
     uint32_t n_cells = 0;  // local table cells
     uint32_t own_begin_cell = 0, own_end_cell = 0;
 
+    // slab decomposition
+    int slab_rank = 0, slab_count = 1;
+    bool has_below = false, has_above = false;
+    uint32_t halo_cap = 0;     // H: capacity (agents) of one two-row ghost strip / message
+    uint32_t array_offset = 0; // first owned agent sits at this index (H if has_below)
+    size_t msg_bytes = 0;
+    uint32_t* d_send_dn = nullptr;     // first two owned rows, for the slab below
+    uint32_t* d_send_up = nullptr;     // last two owned rows, for the slab above
+    uint32_t* d_recv_below = nullptr;  // ghost rows r0-2, r0-1
+    uint32_t* d_recv_above = nullptr;  // ghost rows r1, r1+1
+    pedoni::SlabComm* comm = nullptr;
+    bool halo_pending = false;   // rebuilt, ghosts not exchanged yet (in-process transport)
+    bool halo_inflight = false;  // exchange enqueued on edge_stream, main has not waited on ev_halo
+    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_peer = nullptr;
+
     AgentArrays buf[2]{};
-    uint32_t cap = 0;
+    uint32_t* d_keys[2] = {nullptr, nullptr};  // sort keys, indexed like buf[k]
+    uint32_t cap = 0;          // elements per array
     int cur = 0;
-    uint32_t cur_upper = 0;  // host upper bound of live agents in buf[cur]
-    AgentArrays app{};       // appended spawns, not yet rebuilt
+    uint32_t owned_upper = 0;  // host upper bound of owned agents in buf[cur]
+    AgentArrays app{};         // appended spawns, not yet rebuilt
+    uint32_t* d_keys_app = nullptr;
     uint32_t app_cap = 0, app_n = 0;
 
-    uint32_t* d_keys = nullptr;
     uint32_t* d_ticket = nullptr;
     uint32_t* d_perm = nullptr;
     uint32_t aux_cap = 0;
@@ -70,15 +87,18 @@ struct PedoniModel {
     uint32_t* d_cell_start = nullptr;
     uint32_t* d_tile_sums = nullptr;
     uint32_t n_tiles = 0;
-    uint32_t* d_total = nullptr;
-    uint32_t* d_cur_range = nullptr;  // [begin, end) of owned agents in buf[cur]
+    uint32_t* d_ranges = nullptr;  // [kNumRanges][2], see RangeId
     uint32_t* d_error = nullptr;
     unsigned long long* d_updates = nullptr;
     uint64_t launches = 0;  // kernels launched by this handle
-    uint32_t* h_pub = nullptr;      // pinned, mapped: [begin, end, error] published by the device
-    uint32_t* h_pub_dev = nullptr;  // device alias of h_pub
 
-    bool keys_fresh = false;   // d_keys[0, cur_upper) describe buf[cur]
+    // pinned, mapped: [0] = tick << 32 | n_owned (published after every rebuild)
+    unsigned long long* h_pub = nullptr;
+    unsigned long long* h_pub_dev = nullptr;
+    uint32_t tick = 0;                  // rebuilds (and state resets) so far
+    uint64_t inflow_cum[64] = {0};      // inflow_cum[t % 64]: upper bound of agents added up to tick t
+
+    bool keys_fresh = false;   // d_keys[cur] describe the compute range of buf[cur]
     bool table_valid = false;  // d_cell_start indexes buf[cur]
     bool ever_rebuilt = false;
 
@@ -90,10 +110,11 @@ struct PedoniModel {
     uint64_t acc_force_agents = 0;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
 
-    pedoni::SlabComm* comm = nullptr;
-    int slab_rank = 0, slab_count = 1;
-
     std::string last_error;
+
+    uint32_t n_sides() const { return (has_below ? 1u : 0u) + (has_above ? 1u : 0u); }
+    uint32_t compute_upper() const { return owned_upper + n_sides() * halo_cap; }
+    const uint32_t* range(int id) const { return d_ranges + 2 * id; }
 };
 
 namespace {
@@ -152,34 +173,46 @@ cudaError_t copy_agents(AgentArrays& dst, const AgentArrays& src, uint32_t n, cu
     return cudaSuccess;
 }
 
-// Grow both state buffers (keeping buf[cur]'s first keep_n entries) and the sort scratch.
-int ensure_capacity(PedoniModel* m, uint32_t need) {
-    if (need > m->cap) {
-        uint32_t ncap = std::max<uint32_t>(need, m->cap + m->cap / 2);
+int sync_all(PedoniModel* m) {
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    if (m->edge_stream) CUDA_TRY(m, cudaStreamSynchronize(m->edge_stream));
+    return PEDONI_OK;
+}
+
+// Grow the state buffers (keeping buf[cur] and its keys: the layout uses absolute indices) and the
+// sort scratch. Blocking; only runs when a host upper bound outgrows the allocation.
+int ensure_capacity(PedoniModel* m, uint32_t need_arrays, uint32_t need_aux) {
+    if (need_arrays > m->cap) {
+        int rc = sync_all(m);
+        if (rc != PEDONI_OK) return rc;
+        uint32_t ncap = std::max<uint32_t>(need_arrays, m->cap + m->cap / 2);
         ncap = std::max<uint32_t>(ncap, 1024);
         for (int b = 0; b < 2; ++b) {
             AgentArrays fresh{};
+            uint32_t* fresh_keys = nullptr;
             CUDA_TRY(m, alloc_agents(fresh, ncap));
-            if (b == m->cur && m->cap > 0) CUDA_TRY(m, copy_agents(fresh, m->buf[b], m->cap, m->stream));
+            CUDA_TRY(m, cudaMalloc(&fresh_keys, sizeof(uint32_t) * (size_t)ncap));
+            if (b == m->cur && m->cap > 0) {
+                CUDA_TRY(m, copy_agents(fresh, m->buf[b], m->cap, m->stream));
+                CUDA_TRY(m, cudaMemcpyAsync(fresh_keys, m->d_keys[b], sizeof(uint32_t) * (size_t)m->cap,
+                                            cudaMemcpyDeviceToDevice, m->stream));
+            }
             CUDA_TRY(m, cudaStreamSynchronize(m->stream));
             free_agents(m->buf[b]);
+            cudaFree(m->d_keys[b]);
             m->buf[b] = fresh;
+            m->d_keys[b] = fresh_keys;
         }
         m->cap = ncap;
     }
-    if (need > m->aux_cap) {
-        uint32_t ncap = std::max<uint32_t>(need, m->aux_cap + m->aux_cap / 2);
+    if (need_aux > m->aux_cap) {
+        int rc = sync_all(m);
+        if (rc != PEDONI_OK) return rc;
+        uint32_t ncap = std::max<uint32_t>(need_aux, m->aux_cap + m->aux_cap / 2);
         ncap = std::max<uint32_t>(ncap, 1024);
-        uint32_t* nk = nullptr;
-        CUDA_TRY(m, cudaMalloc(&nk, sizeof(uint32_t) * (size_t)ncap));
-        if (m->d_keys && m->aux_cap)
-            CUDA_TRY(m, cudaMemcpyAsync(nk, m->d_keys, sizeof(uint32_t) * (size_t)m->aux_cap, cudaMemcpyDeviceToDevice,
-                                        m->stream));
-        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
-        cudaFree(m->d_keys);
         cudaFree(m->d_ticket);
         cudaFree(m->d_perm);
-        m->d_keys = nk;
+        m->d_ticket = m->d_perm = nullptr;
         CUDA_TRY(m, cudaMalloc(&m->d_ticket, sizeof(uint32_t) * (size_t)ncap));
         CUDA_TRY(m, cudaMalloc(&m->d_perm, sizeof(uint32_t) * (size_t)ncap));
         m->aux_cap = ncap;
@@ -192,11 +225,15 @@ int ensure_app_capacity(PedoniModel* m, uint32_t need) {
     uint32_t ncap = std::max<uint32_t>(need, m->app_cap * 2);
     ncap = std::max<uint32_t>(ncap, 1024);
     AgentArrays fresh{};
+    uint32_t* fresh_keys = nullptr;
     CUDA_TRY(m, alloc_agents(fresh, ncap));
+    CUDA_TRY(m, cudaMalloc(&fresh_keys, sizeof(uint32_t) * (size_t)ncap));
     CUDA_TRY(m, copy_agents(fresh, m->app, m->app_n, m->stream));
     CUDA_TRY(m, cudaStreamSynchronize(m->stream));
     free_agents(m->app);
+    cudaFree(m->d_keys_app);
     m->app = fresh;
+    m->d_keys_app = fresh_keys;
     m->app_cap = ncap;
     return PEDONI_OK;
 }
@@ -216,25 +253,28 @@ cudaEvent_t take_event(PedoniModel* m) {
 struct ScopedTimer {
     PedoniModel* m;
     TimedLaunch t{};
+    cudaStream_t s;
     bool on;
-    ScopedTimer(PedoniModel* m_, int kind, uint64_t agents = 0) : m(m_), on(m_->profiling) {
+    ScopedTimer(PedoniModel* m_, int kind, cudaStream_t stream, uint64_t agents = 0)
+        : m(m_), s(stream), on(m_->profiling) {
         if (!on) return;
         t.kind = kind;
         t.agents = agents;
         t.start = take_event(m);
         t.stop = take_event(m);
-        cudaEventRecord(t.start, m->stream);
+        cudaEventRecord(t.start, s);
     }
     ~ScopedTimer() {
         if (!on) return;
-        cudaEventRecord(t.stop, m->stream);
+        cudaEventRecord(t.stop, s);
         m->timed.push_back(t);
     }
 };
 
 int drain_timed(PedoniModel* m) {
     if (m->timed.empty()) return PEDONI_OK;
-    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    int rc = sync_all(m);
+    if (rc != PEDONI_OK) return rc;
     for (auto& t : m->timed) {
         float ms = 0.f;
         CUDA_TRY(m, cudaEventElapsedTime(&ms, t.start, t.stop));
@@ -289,59 +329,127 @@ void build_edges(const float* obstacles, int n, std::vector<float>& out) {
     }
 }
 
+// Sort input = [compute range of buf[cur]] ++ [appended spawns]: "previous index" order.
 SortInput make_sort_input(PedoniModel* m) {
     SortInput in{};
     in.nseg = 2;
-    in.seg[0] = Segment{m->buf[m->cur], m->d_cur_range, m->cur_upper};
-    in.seg[1] = Segment{m->app, nullptr, m->app_n};
+    in.seg[0] = Segment{m->buf[m->cur], m->d_keys[m->cur], m->range(kRangeCompute), m->compute_upper()};
+    in.seg[1] = Segment{m->app, m->d_keys_app, nullptr, m->app_n};
     in.prefix[0] = 0;
-    in.prefix[1] = m->cur_upper;
-    in.prefix[2] = m->cur_upper + m->app_n;
-    for (int k = 3; k <= kMaxSegments; ++k) in.prefix[k] = in.prefix[2];
+    in.prefix[1] = m->compute_upper();
+    in.prefix[2] = m->compute_upper() + m->app_n;
     return in;
 }
 
 template <Math M, bool D>
-void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem) {
-    force_integrate_kernel<M, D><<<blocks, 128, smem, m->stream>>>(p);
+void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem, cudaStream_t s) {
+    force_integrate_kernel<M, D><<<blocks, 128, smem, s>>>(p);
     m->launches += 1;
 }
 
-void launch_force(PedoniModel* m, const ForceParams& p) {
-    const uint32_t blocks = div_up(p.count_upper, 128);
+void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream_t s) {
+    const uint32_t blocks = div_up(count_upper, 128);
     if (blocks == 0) return;
+    ForceParams p{};
+    p.in = m->buf[m->cur];
+    p.out = m->buf[m->cur ^ 1];
+    p.d_range = m->range(range_id);
+    p.d_owned = m->range(kRangeOwned);
+    p.count_upper = count_upper;
+    p.cell_start = m->d_cell_start;
+    p.grid = m->grid;
+    p.field = m->field;
+    p.keys_out = m->d_keys[m->cur ^ 1];
+    p.error_flag = m->d_error;
+    p.updates_total = m->d_updates;
+    p.obstacle_edges = m->d_edges;
+    p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
     const size_t smem = m->use_distance_map ? 0 : sizeof(float) * 64 * kEdgeFloats;
+    ScopedTimer t(m, kForce, s, count_upper);
     if (m->math_mode == PEDONI_MATH_STRICT) {
         if (m->use_distance_map)
-            launch_force_t<Math::Strict, true>(m, p, blocks, smem);
+            launch_force_t<Math::Strict, true>(m, p, blocks, smem, s);
         else
-            launch_force_t<Math::Strict, false>(m, p, blocks, smem);
+            launch_force_t<Math::Strict, false>(m, p, blocks, smem, s);
     } else {
         if (m->use_distance_map)
-            launch_force_t<Math::Fast, true>(m, p, blocks, smem);
+            launch_force_t<Math::Fast, true>(m, p, blocks, smem, s);
         else
-            launch_force_t<Math::Fast, false>(m, p, blocks, smem);
+            launch_force_t<Math::Fast, false>(m, p, blocks, smem, s);
     }
 }
 
+// Blocking: callers have synchronised (or are about to block anyway).
 int check_device_error(PedoniModel* m) {
-    if (m->h_pub[2] != 0) {
-        m->h_pub[2] = 0;
-        cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream);
+    uint32_t bits = 0;
+    CUDA_TRY(m, cudaMemcpyAsync(&bits, m->d_error, sizeof bits, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    if (bits == 0) return PEDONI_OK;
+    CUDA_TRY(m, cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
+    if (bits & kErrBadDestination)
         return fail(m, PEDONI_ERR_INVALID,
                     "device flagged an invalid agent (destination >= n_potential_maps); the reference would panic "
                     "with an index-out-of-bounds at field.rs:237");
-    }
-    return PEDONI_OK;
+    if (bits & kErrHaloOverflow)
+        return fail(m, PEDONI_ERR_CAPACITY,
+                    "two boundary rows of a slab hold more than halo_capacity = %u agents (or the ghost strip "
+                    "overran the arrays); raise PedoniConfig.halo_capacity", m->halo_cap);
+    return fail(m, PEDONI_ERR_STATE,
+                "a pedestrian crossed two or more neighbor-grid rows in one step; the slab decomposition "
+                "exchanges two ghost rows per tick and cannot follow it (speed > %.1f m/s)",
+                m->grid.unit / 0.1f);
 }
 
-__global__ void publish_error_kernel(const uint32_t* d_error, uint32_t* h_slot) { *h_slot = *d_error; }
+__global__ void reset_layout_kernel(uint32_t* ranges, uint32_t offset, unsigned long long* host_slot, uint32_t tick) {
+    for (int k = 0; k < 2 * kNumRanges; ++k) ranges[k] = offset;
+    *host_slot = static_cast<unsigned long long>(tick) << 32;
+}
 
-__global__ void set_range_kernel(uint32_t* d_range, uint32_t* host_slot, uint32_t b, uint32_t e) {
-    d_range[0] = b;
-    d_range[1] = e;
-    host_slot[0] = b;
-    host_slot[1] = e;
+// Upper bound of the owned population after the rebuild that just became tick m->tick: the last count
+// the device published (it may lag the host by a few ticks) plus everything that can have been added
+// since. Never synchronises.
+uint32_t owned_bound(PedoniModel* m, uint32_t sort_input_upper) {
+    const unsigned long long pub = *reinterpret_cast<volatile unsigned long long*>(m->h_pub);
+    const uint32_t pub_tick = static_cast<uint32_t>(pub >> 32), pub_n = static_cast<uint32_t>(pub);
+    uint64_t bound = sort_input_upper;
+    if (pub_tick <= m->tick && m->tick - pub_tick < 64) {
+        const uint64_t since = m->inflow_cum[m->tick % 64] - m->inflow_cum[pub_tick % 64];
+        bound = std::min<uint64_t>(bound, pub_n + since);
+    }
+    return static_cast<uint32_t>(bound);
+}
+
+void advance_tick(PedoniModel* m, uint64_t inflow) {
+    const uint64_t prev = m->inflow_cum[m->tick % 64];
+    m->tick += 1;
+    m->inflow_cum[m->tick % 64] = prev + inflow;
+}
+
+HaloMessage msg_of(uint32_t* words) { return HaloMessage{words}; }
+
+// Enqueue the ghost unpack (edge stream) once both strips have landed in d_recv_*.
+void enqueue_unpack(PedoniModel* m) {
+    const uint32_t threads = std::max<uint32_t>(m->halo_cap, 2 * m->grid.nx + 1);
+    dim3 grid(div_up(threads, 256), 2);
+    halo_unpack_kernel<<<grid, 256, 0, m->edge_stream>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell,
+                                                         m->own_end_cell, m->grid.nx, m->halo_cap, m->cap,
+                                                         msg_of(m->d_recv_below), msg_of(m->d_recv_above),
+                                                         m->has_below, m->has_above, m->d_ranges, m->d_error);
+    m->launches += 1;
+    cudaEventRecord(m->ev_halo, m->edge_stream);
+    m->halo_pending = false;
+    m->halo_inflight = true;
+}
+
+int exchange_nccl(PedoniModel* m) {
+    CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, m->ev_packed, 0));
+    ScopedTimer t(m, kComm, m->edge_stream);
+    std::string err;
+    int rc = pedoni::slab_comm_exchange(m->comm, m->edge_stream, m->d_send_dn, m->d_recv_below, m->d_send_up,
+                                        m->d_recv_above, m->msg_bytes, m->has_below, m->has_above, &err);
+    if (rc != PEDONI_OK) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
+    enqueue_unpack(m);
+    return PEDONI_OK;
 }
 
 }  // namespace
@@ -431,20 +539,45 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     m->slab_rank = m->slab_count > 1 ? c->slab_rank : 0;
     int32_t r0 = 0, r1 = m->grid.ny;
     if (m->slab_count > 1) {
-        if (pedoni_slab_rows(m->grid.ny, m->slab_count, m->slab_rank, &r0, &r1) != PEDONI_OK || r1 - r0 < 1) {
-            fail(m, PEDONI_ERR_INVALID, "slab %d of %d owns no rows of a %d-row grid", m->slab_rank, m->slab_count,
-                 m->grid.ny);
+        // every slab ships two whole rows to each neighbour, so it must own at least two
+        if (pedoni_slab_rows(m->grid.ny, m->slab_count, m->slab_rank, &r0, &r1) != PEDONI_OK ||
+            m->grid.ny / m->slab_count < 2) {
+            fail(m, PEDONI_ERR_INVALID, "slab %d of %d: a %d-row grid gives a slab fewer than 2 rows", m->slab_rank,
+                 m->slab_count, m->grid.ny);
             return bail(PEDONI_ERR_INVALID);
         }
+        m->has_below = m->slab_rank > 0;
+        m->has_above = m->slab_rank < m->slab_count - 1;
     }
+    m->grid.slab = m->slab_count > 1 ? 1 : 0;
     m->grid.own_row0 = r0;
     m->grid.own_row1 = r1;
-    m->grid.row_base = std::max(r0 - 1, 0);
-    const int table_end = std::min(r1 + 1, m->grid.ny);
+    m->grid.row_base = r0 - (m->has_below ? 2 : 0);
+    const int table_end = r1 + (m->has_above ? 2 : 0);
     m->grid.table_rows = table_end - m->grid.row_base;
     m->n_cells = static_cast<uint32_t>(m->grid.table_rows) * static_cast<uint32_t>(m->grid.nx);
     m->own_begin_cell = static_cast<uint32_t>(r0 - m->grid.row_base) * m->grid.nx;
     m->own_end_cell = static_cast<uint32_t>(r1 - m->grid.row_base) * m->grid.nx;
+
+    const uint32_t capacity = c->capacity ? c->capacity : 4096;
+    if (m->slab_count > 1) {
+        if (c->halo_capacity) {
+            m->halo_cap = c->halo_capacity;
+        } else {  // 4x the two-row population of a uniformly filled slab
+            const uint64_t per_row = capacity / static_cast<uint32_t>(r1 - r0) + 1;
+            m->halo_cap = static_cast<uint32_t>(std::max<uint64_t>(4096, 8 * per_row));
+        }
+        m->halo_cap = (m->halo_cap + 255u) & ~255u;
+        m->array_offset = m->has_below ? m->halo_cap : 0;
+        m->msg_bytes = halo_message_words(m->grid.nx, m->halo_cap) * sizeof(uint32_t);
+        CREATE_TRY(cudaStreamCreateWithFlags(&m->edge_stream, cudaStreamNonBlocking));
+        for (uint32_t** b : {&m->d_send_dn, &m->d_send_up, &m->d_recv_below, &m->d_recv_above}) {
+            CREATE_TRY(cudaMalloc(b, m->msg_bytes));
+            CREATE_TRY(cudaMemsetAsync(*b, 0, m->msg_bytes, m->stream));
+        }
+        for (cudaEvent_t* e : {&m->ev_packed, &m->ev_halo, &m->ev_edge, &m->ev_peer})
+            CREATE_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
 
     // Field (field.rs:194-205)
     m->field.unit = c->field_grid_unit;
@@ -476,21 +609,21 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     CREATE_TRY(cudaMalloc(&m->d_cell_count, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
     CREATE_TRY(cudaMalloc(&m->d_cell_start, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
     CREATE_TRY(cudaMalloc(&m->d_tile_sums, sizeof(uint32_t) * std::max<uint32_t>(m->n_tiles, 1)));
-    CREATE_TRY(cudaMalloc(&m->d_total, sizeof(uint32_t)));
-    CREATE_TRY(cudaMalloc(&m->d_cur_range, sizeof(uint32_t) * 2));
+    CREATE_TRY(cudaMalloc(&m->d_ranges, sizeof(uint32_t) * 2 * kNumRanges));
     CREATE_TRY(cudaMalloc(&m->d_error, sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&m->d_updates, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(m->d_updates, 0, sizeof(unsigned long long), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_cell_start, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
-    CREATE_TRY(cudaMemsetAsync(m->d_cur_range, 0, sizeof(uint32_t) * 2, m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
-    CREATE_TRY(cudaHostAlloc(&m->h_pub, sizeof(uint32_t) * 4, cudaHostAllocMapped));
-    std::memset(m->h_pub, 0, sizeof(uint32_t) * 4);
+    CREATE_TRY(cudaHostAlloc(&m->h_pub, sizeof(unsigned long long) * 2, cudaHostAllocMapped));
+    m->h_pub[0] = m->h_pub[1] = 0;
     CREATE_TRY(cudaHostGetDevicePointer(&m->h_pub_dev, m->h_pub, 0));
+    reset_layout_kernel<<<1, 1, 0, m->stream>>>(m->d_ranges, m->array_offset, m->h_pub_dev, m->tick);
     CREATE_TRY(cudaEventCreate(&m->timer_start));
     CREATE_TRY(cudaEventCreate(&m->timer_stop));
 
-    if (ensure_capacity(m, c->capacity ? c->capacity : 4096) != PEDONI_OK) return bail(PEDONI_ERR_CUDA);
+    if (ensure_capacity(m, m->array_offset + capacity + (m->has_above ? m->halo_cap : 0), capacity) != PEDONI_OK)
+        return bail(PEDONI_ERR_CUDA);
     CREATE_TRY(cudaStreamSynchronize(m->stream));  // borrowed map pointers may die after return
 #undef CREATE_TRY
     *out = m;
@@ -501,31 +634,26 @@ void pedoni_destroy(PedoniModel* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->edge_stream) cudaStreamSynchronize(m->edge_stream);
     if (m->comm) pedoni::slab_comm_destroy(m->comm);
     for (auto& t : m->timed) {
         cudaEventDestroy(t.start);
         cudaEventDestroy(t.stop);
     }
     for (auto e : m->event_pool) cudaEventDestroy(e);
-    if (m->timer_start) cudaEventDestroy(m->timer_start);
-    if (m->timer_stop) cudaEventDestroy(m->timer_stop);
+    for (cudaEvent_t e : {m->timer_start, m->timer_stop, m->ev_packed, m->ev_halo, m->ev_edge, m->ev_peer})
+        if (e) cudaEventDestroy(e);
     free_agents(m->buf[0]);
     free_agents(m->buf[1]);
     free_agents(m->app);
-    cudaFree(m->d_keys);
-    cudaFree(m->d_ticket);
-    cudaFree(m->d_perm);
-    cudaFree(m->d_cell_count);
-    cudaFree(m->d_cell_start);
-    cudaFree(m->d_tile_sums);
-    cudaFree(m->d_total);
-    cudaFree(m->d_cur_range);
-    cudaFree(m->d_error);
-    cudaFree(m->d_updates);
-    cudaFree(m->d_distance);
-    cudaFree(m->d_potential);
-    cudaFree(m->d_edges);
+    for (void* p : {(void*)m->d_keys[0], (void*)m->d_keys[1], (void*)m->d_keys_app, (void*)m->d_ticket, (void*)m->d_perm,
+                    (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_sums, (void*)m->d_ranges,
+                    (void*)m->d_error, (void*)m->d_updates, (void*)m->d_distance, (void*)m->d_potential,
+                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_recv_below,
+                    (void*)m->d_recv_above})
+        cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
+    if (m->edge_stream) cudaStreamDestroy(m->edge_stream);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -533,7 +661,8 @@ void pedoni_destroy(PedoniModel* m) {
 int pedoni_synchronize(PedoniModel* m) {
     if (!m) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
-    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    int rc = sync_all(m);
+    if (rc != PEDONI_OK) return rc;
     return check_device_error(m);
 }
 
@@ -541,7 +670,8 @@ static int append_agents(PedoniModel* m, uint32_t n, const float* pos_xy, const 
                          const float* v0) {
     if (n == 0) return PEDONI_OK;
     if (!pos_xy || !dest || !v0) return fail(m, PEDONI_ERR_INVALID, "null agent array with n = %u", n);
-    if ((uint64_t)m->cur_upper + m->app_n + n > 0xFFFFFFF0ull) return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
+    if ((uint64_t)m->array_offset + m->compute_upper() + m->app_n + n + m->halo_cap > 0xFFFFFFF0ull)
+        return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
     int rc = ensure_app_capacity(m, m->app_n + n);
     if (rc != PEDONI_OK) return rc;
     const uint32_t at = m->app_n;
@@ -575,73 +705,159 @@ int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const u
     if (!m) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
     if (n > 0 && !vel_xy) return fail(m, PEDONI_ERR_INVALID, "null velocity array");
-    set_range_kernel<<<1, 1, 0, m->stream>>>(m->d_cur_range, m->h_pub_dev, 0u, 0u);
-    m->cur_upper = 0;
+    if (m->halo_inflight) {
+        CUDA_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+        m->halo_inflight = false;
+    }
+    advance_tick(m, 0);
+    reset_layout_kernel<<<1, 1, 0, m->stream>>>(m->d_ranges, m->array_offset, m->h_pub_dev, m->tick);
+    m->launches += 1;
+    m->owned_upper = 0;
     m->app_n = 0;
     m->keys_fresh = false;
     m->table_valid = false;
+    m->halo_pending = false;
+    // compute_upper() still counts ghost capacity, but every range is empty now: nothing is adopted.
     return append_agents(m, n, pos_xy, dest, vel_xy, v0);
+}
+
+static int rebuild_impl(PedoniModel* m) {
+    cudaStream_t s = m->stream;
+    const uint32_t resident = m->compute_upper();
+    const uint32_t total = resident + m->app_n;
+    const uint64_t need = (uint64_t)m->array_offset + total + (m->has_above ? m->halo_cap : 0);
+    if (need > 0xFFFFFFF0ull) return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
+    int rc = ensure_capacity(m, static_cast<uint32_t>(need), std::max<uint32_t>(total, 1));
+    if (rc != PEDONI_OK) return rc;
+    SortInput in = make_sort_input(m);
+
+    if (total > 0) {
+        const uint32_t t_begin = m->keys_fresh ? resident : 0u;
+        if (t_begin < total) {
+            ScopedTimer t(m, kKey, s);
+            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field, m->d_error);
+            m->launches += 1;
+        }
+    }
+    {
+        ScopedTimer t(m, kHistogram, s);
+        CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
+        if (total > 0) {
+            histogram_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_count, m->d_ticket);
+            m->launches += 1;
+        }
+    }
+    {
+        ScopedTimer t(m, kScan, s);
+        scan_reduce_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums);
+        scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(m->d_tile_sums, m->n_tiles);
+        scan_apply_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums,
+                                                              m->array_offset, m->d_cell_start);
+        m->launches += 3;
+    }
+    if (total > 0) {
+        {
+            ScopedTimer t(m, kScatter, s);
+            scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_ticket, m->d_cell_start, m->d_perm);
+            m->launches += 1;
+        }
+        {
+            ScopedTimer t(m, kGather, s);
+            gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_ticket, m->d_cell_start, m->d_perm,
+                                                            m->buf[m->cur ^ 1]);
+            m->launches += 1;
+        }
+    }
+    advance_tick(m, (uint64_t)m->app_n + (uint64_t)m->n_sides() * m->halo_cap);
+    publish_layout_kernel<<<1, 1, 0, s>>>(m->d_cell_start, m->own_begin_cell, m->own_end_cell, m->grid.nx,
+                                          m->has_below, m->has_above, m->d_ranges, m->h_pub_dev, m->tick);
+    m->launches += 1;
+
+    m->cur ^= 1;
+    m->owned_upper = owned_bound(m, total);
+    m->app_n = 0;
+    m->keys_fresh = false;
+    m->table_valid = true;
+    m->ever_rebuilt = true;
+
+    if (m->slab_count > 1) {
+        const uint32_t threads = std::max<uint32_t>(m->halo_cap, 2 * m->grid.nx + 1);
+        dim3 grid(div_up(threads, 256), 2);
+        halo_pack_kernel<<<grid, 256, 0, s>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell, m->own_end_cell,
+                                              m->grid.nx, m->halo_cap, msg_of(m->d_send_dn), msg_of(m->d_send_up),
+                                              m->has_below, m->has_above, m->tick, m->d_error);
+        m->launches += 1;
+        CUDA_TRY(m, cudaEventRecord(m->ev_packed, s));
+        m->halo_pending = true;
+        if (m->comm) {
+            rc = exchange_nccl(m);
+            if (rc != PEDONI_OK) return rc;
+        }
+    }
+    CUDA_TRY(m, cudaGetLastError());
+    return PEDONI_OK;
 }
 
 int pedoni_rebuild(PedoniModel* m) {
     if (!m) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
-    const uint32_t total = m->cur_upper + m->app_n;
-    int rc = ensure_capacity(m, std::max<uint32_t>(total, 1));
-    if (rc != PEDONI_OK) return rc;
-    cudaStream_t s = m->stream;
-    SortInput in = make_sort_input(m);
+    if (m->halo_inflight) {  // rebuild without a step in between: the compute range is still being written
+        CUDA_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+        m->halo_inflight = false;
+    }
+    // Worst case every input agent is kept; ghosts from above land right behind them.
+    const uint64_t need = (uint64_t)m->array_offset + m->compute_upper() + m->app_n + (m->has_above ? m->halo_cap : 0);
+    if (need > m->cap) {
+        // The host bound may be stale: refresh it with the exact population before growing anything.
+        int rc = sync_all(m);
+        if (rc != PEDONI_OK) return rc;
+        m->owned_upper = std::min<uint32_t>(m->owned_upper, static_cast<uint32_t>(m->h_pub[0]));
+    }
+    return rebuild_impl(m);
+}
 
-    if (total > 0) {
-        const uint32_t t_begin = m->keys_fresh ? m->cur_upper : 0u;
-        if (t_begin < total) {
-            ScopedTimer t(m, kKey);
-            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field, m->d_keys,
-                                                                   m->d_error, /*foreign_rows_drop=*/true);
-            m->launches += 1;
-        }
+int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n) {
+    if (!models || n < 1) return PEDONI_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+        PedoniModel* m = models[i];
+        if (!m) return PEDONI_ERR_INVALID;
+        if (m->slab_count != n || m->slab_rank != i)
+            return fail(m, PEDONI_ERR_INVALID, "models[%d] is slab %d of %d, expected %d of %d", i, m->slab_rank,
+                        m->slab_count, i, n);
+        if (m->comm) return fail(m, PEDONI_ERR_STATE, "handle exchanges over NCCL; the in-process transport is for "
+                                                       "handles without pedoni_comm_init");
+        if (n > 1 && !m->halo_pending) return fail(m, PEDONI_ERR_STATE, "no rebuild pending an exchange");
+        if (i > 0 && (models[i - 1]->msg_bytes != m->msg_bytes))
+            return fail(m, PEDONI_ERR_INVALID, "slabs disagree on the halo message size (halo_capacity)");
     }
-    {
-        ScopedTimer t(m, kHistogram);
-        CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
-        if (total > 0) {
-            histogram_kernel<<<div_up(total, 256), 256, 0, s>>>(total, m->d_keys, m->d_cell_count, m->d_ticket);
-            m->launches += 1;
+    if (n == 1) return PEDONI_OK;
+    // Strip copies run on the RECEIVER's edge stream, after the sender's pack.
+    for (int i = 0; i < n; ++i) {
+        PedoniModel* m = models[i];
+        CUDA_TRY(m, cudaSetDevice(m->device));
+        CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, m->ev_packed, 0));
+        if (m->has_below) {
+            PedoniModel* o = models[i - 1];
+            CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, o->ev_packed, 0));
+            CUDA_TRY(m, cudaMemcpyAsync(m->d_recv_below, o->d_send_up, m->msg_bytes, cudaMemcpyDefault, m->edge_stream));
         }
-    }
-    {
-        ScopedTimer t(m, kScan);
-        scan_reduce_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums);
-        scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(m->d_tile_sums, m->n_tiles, m->d_total);
-        scan_apply_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums,
-                                                              m->d_cell_start);
-        m->launches += 3;
-    }
-    if (total > 0) {
-        {
-            ScopedTimer t(m, kScatter);
-            scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(total, m->d_keys, m->d_ticket, m->d_cell_start, m->d_perm);
-            m->launches += 1;
+        if (m->has_above) {
+            PedoniModel* o = models[i + 1];
+            CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, o->ev_packed, 0));
+            CUDA_TRY(m, cudaMemcpyAsync(m->d_recv_above, o->d_send_dn, m->msg_bytes, cudaMemcpyDefault, m->edge_stream));
         }
-        {
-            ScopedTimer t(m, kGather);
-            gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_keys, m->d_cell_start, m->d_perm,
-                                                            m->buf[m->cur ^ 1]);
-            m->launches += 1;
-        }
+        CUDA_TRY(m, cudaEventRecord(m->ev_peer, m->edge_stream));
     }
-    publish_range_kernel<<<1, 1, 0, s>>>(m->d_cell_start, m->own_begin_cell, m->own_end_cell, m->d_cur_range,
-                                         m->h_pub_dev);
-    publish_error_kernel<<<1, 1, 0, s>>>(m->d_error, m->h_pub_dev + 2);
-    m->launches += 2;
-    CUDA_TRY(m, cudaGetLastError());
-
-    m->cur ^= 1;
-    m->cur_upper = total;
-    m->app_n = 0;
-    m->keys_fresh = false;
-    m->table_valid = true;
-    m->ever_rebuilt = true;
+    // A sender may not repack (next tick, its main stream) before its neighbours have read the strips:
+    // its edge stream waits for their copies, and its main stream waits for its edge stream every step.
+    for (int i = 0; i < n; ++i) {
+        PedoniModel* m = models[i];
+        CUDA_TRY(m, cudaSetDevice(m->device));
+        if (m->has_below) CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, models[i - 1]->ev_peer, 0));
+        if (m->has_above) CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, models[i + 1]->ev_peer, 0));
+        enqueue_unpack(m);
+        CUDA_TRY(m, cudaGetLastError());
+    }
     return PEDONI_OK;
 }
 
@@ -650,40 +866,37 @@ int pedoni_step(PedoniModel* m) {
     CUDA_TRY(m, cudaSetDevice(m->device));
     if (m->app_n > 0 || !m->table_valid)
         return fail(m, PEDONI_ERR_STATE,
-                    "pedoni_step needs a rebuilt neighbor grid: call pedoni_rebuild after pedoni_spawn / "
-                    "pedoni_upload_state (the reference rebuilds inside spawn_pedestrians, sfm.rs:58-77)");
-    if (m->cur_upper > 0) {
-        ForceParams p{};
-        p.in = m->buf[m->cur];
-        p.out = m->buf[m->cur ^ 1];
-        p.d_range = m->d_cur_range;
-        p.first = 0;
-        p.count_upper = m->cur_upper;
-        p.cell_start = m->d_cell_start;
-        p.grid = m->grid;
-        p.field = m->field;
-        p.keys_out = m->d_keys;
-        p.key_base = 0;
-        p.error_flag = m->d_error;
-        p.updates_total = m->d_updates;
-        p.obstacle_edges = m->d_edges;
-        p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
-        ScopedTimer t(m, kForce, m->cur_upper);
-        launch_force(m, p);
+                    "pedoni_step needs a freshly rebuilt neighbor grid: call pedoni_rebuild before every "
+                    "pedoni_step and after pedoni_spawn / pedoni_upload_state (the reference rebuilds inside "
+                    "spawn_pedestrians every tick, sfm.rs:58-77, lib.rs:85-90)");
+    if (m->halo_pending)
+        return fail(m, PEDONI_ERR_STATE,
+                    "slab %d of %d has no ghost rows for this tick: join the ranks with pedoni_comm_init, or call "
+                    "pedoni_slab_exchange_local after every handle's pedoni_rebuild", m->slab_rank, m->slab_count);
+    // Interior rows need no ghost data: they run on the main stream while the halo is still in flight.
+    launch_force(m, kRangeInterior, m->owned_upper, m->stream);
+    if (m->slab_count > 1) {
+        if (m->has_below) launch_force(m, kRangeEdgeLo, 2 * m->halo_cap, m->edge_stream);
+        if (m->has_above) launch_force(m, kRangeEdgeHi, 2 * m->halo_cap, m->edge_stream);
+        CUDA_TRY(m, cudaEventRecord(m->ev_edge, m->edge_stream));
+        CUDA_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_edge, 0));
+        m->halo_inflight = false;  // ev_edge is behind ev_halo on the edge stream
     }
     CUDA_TRY(m, cudaGetLastError());
     m->cur ^= 1;
     m->keys_fresh = true;
+    m->table_valid = false;  // positions moved; the reference, too, rebuilds before every update (lib.rs:85-90)
     return PEDONI_OK;
 }
 
-// Blocks; refreshes the host's knowledge of the live range.
+// Blocks; returns the owned range of buf[cur].
 static int sync_range(PedoniModel* m, uint32_t* begin, uint32_t* end) {
-    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
-    int rc = check_device_error(m);
+    int rc = sync_all(m);
     if (rc != PEDONI_OK) return rc;
-    *begin = m->h_pub[0];
-    *end = m->h_pub[1];
+    rc = check_device_error(m);
+    if (rc != PEDONI_OK) return rc;
+    *begin = m->array_offset;
+    *end = m->array_offset + static_cast<uint32_t>(m->h_pub[0]);
     return PEDONI_OK;
 }
 
@@ -741,10 +954,12 @@ int pedoni_cell_table(PedoniModel* m, uint32_t* indices, uint32_t cap, uint32_t*
     const uint32_t n = m->own_end_cell - m->own_begin_cell + 1;
     if (n_out) *n_out = n;
     if (cap < n || !indices) return fail(m, PEDONI_ERR_CAPACITY, "cell table needs %u entries", n);
+    int rc = sync_all(m);
+    if (rc != PEDONI_OK) return rc;
     CUDA_TRY(m, cudaMemcpyAsync(indices, m->d_cell_start + m->own_begin_cell, sizeof(uint32_t) * (size_t)n,
                                 cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(m, cudaStreamSynchronize(m->stream));
-    const uint32_t base = indices[0];  // local offsets: halo agents below the owned rows do not count
+    const uint32_t base = indices[0];  // local offsets: the first owned agent is entry 0
     if (base)
         for (uint32_t k = 0; k < n; ++k) indices[k] -= base;
     return PEDONI_OK;
@@ -797,6 +1012,8 @@ int pedoni_counters(PedoniModel* m, uint64_t* kernel_launches, uint64_t* pedestr
     if (kernel_launches) *kernel_launches = m->launches;
     if (pedestrian_updates) {
         unsigned long long v = 0;
+        int rc = sync_all(m);
+        if (rc != PEDONI_OK) return rc;
         CUDA_TRY(m, cudaMemcpyAsync(&v, m->d_updates, sizeof v, cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(m, cudaStreamSynchronize(m->stream));
         *pedestrian_updates = v;
@@ -812,6 +1029,10 @@ int pedoni_timer_begin(PedoniModel* m) {
 int pedoni_timer_end(PedoniModel* m, float* ms) {
     if (!m || !ms) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
+    if (m->halo_inflight) {  // the last rebuild's exchange belongs to the timed region
+        CUDA_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_halo, 0));
+        m->halo_inflight = false;
+    }
     CUDA_TRY(m, cudaEventRecord(m->timer_stop, m->stream));
     CUDA_TRY(m, cudaEventSynchronize(m->timer_stop));
     CUDA_TRY(m, cudaEventElapsedTime(ms, m->timer_start, m->timer_stop));
@@ -829,9 +1050,16 @@ int pedoni_comm_init(PedoniModel* m, const void* id128) {
     if (!m || !id128) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
     if (m->slab_count <= 1) return fail(m, PEDONI_ERR_STATE, "pedoni_comm_init on a whole-domain handle");
+    if (m->comm) return fail(m, PEDONI_ERR_STATE, "communicator already initialised");
     std::string err;
     m->comm = pedoni::slab_comm_create(id128, m->slab_rank, m->slab_count, &err);
     if (!m->comm) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
+    if (m->halo_pending) return exchange_nccl(m);  // a rebuild was already waiting for its ghosts
+    return PEDONI_OK;
+}
+int pedoni_halo_capacity(const PedoniModel* m, uint32_t* halo_capacity) {
+    if (!m || !halo_capacity) return PEDONI_ERR_INVALID;
+    *halo_capacity = m->halo_cap;
     return PEDONI_OK;
 }
 

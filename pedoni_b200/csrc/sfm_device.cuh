@@ -177,34 +177,39 @@ struct GridView {
     int table_rows;  // rows covered by the local cell table (ny on a whole-domain handle)
     int own_row0;    // global rows [own_row0, own_row1) are owned by this handle
     int own_row1;
+    int slab;        // 1 on a slab handle (ghost rows exist), 0 on a whole-domain handle
 };
 
-constexpr uint32_t kKeyDrop = 0xFFFFFFFFu;         // out of grid, despawned, or not ours
-constexpr uint32_t kKeyMigrateDown = 0xFFFFFFFEu;  // alive, now in a row below own_row0 (slabs)
-constexpr uint32_t kKeyMigrateUp = 0xFFFFFFFDu;    // alive, now in a row >= own_row1 (slabs)
+constexpr uint32_t kKeyDrop = 0xFFFFFFFFu;  // out of grid, despawned, or in a row this handle does not own
 constexpr uint32_t kKeyFirstSpecial = 0xFFFFFFF0u;
+
+// Device error flag bits (PedoniModel::d_error).
+constexpr uint32_t kErrBadDestination = 1u;  // destination >= n_potential_maps (reference: index panic, field.rs:237)
+constexpr uint32_t kErrRowJump = 2u;         // slab handle: a pedestrian crossed >= 2 grid rows in one step
+constexpr uint32_t kErrHaloOverflow = 4u;    // slab handle: two boundary rows hold more agents than halo_capacity
 
 // `(pos / unit).as_ivec2()` (neighbor_grid.rs:27, sfm.rs:113): IEEE divide, truncate toward zero.
 __device__ __forceinline__ int2 cell_of(float2 pos, float unit) {
     return make_int2(__float2int_rz(S::div(pos.x, unit)), __float2int_rz(S::div(pos.y, unit)));
 }
 
-// Sort key of an agent for the next rebuild: local cell id, or a special.
+// Sort key of an agent for the next rebuild: local cell id, or kKeyDrop.
 //  - outside the grid -> dropped (neighbor_grid.rs:29-33, util.rs:31)
 //  - potential(dest, pos) > 0.25 is false (incl. NaN) -> despawned (sfm.rs:69)
 //  - destination >= n_maps would panic in the reference (index out of bounds); here it drops the
 //    agent and raises the device error flag.
+//  - slab handles: an agent whose row belongs to another slab is dropped HERE; the owner of that row
+//    integrates the same agent redundantly (it holds it as a ghost) and adopts it in its own rebuild.
 __device__ __forceinline__ uint32_t sort_key(const GridView& g, const FieldView& f, float2 pos, uint32_t dest,
                                              uint32_t* error_flag) {
     int2 c = cell_of(pos, g.unit);
     if (c.x < 0 || c.y < 0 || c.x >= g.nx || c.y >= g.ny) return kKeyDrop;
     if (dest >= static_cast<uint32_t>(f.n_maps)) {
-        atomicOr(error_flag, 1u);
+        atomicOr(error_flag, kErrBadDestination);
         return kKeyDrop;
     }
     if (!(get_potential(f, dest, pos) > 0.25f)) return kKeyDrop;
-    if (c.y < g.own_row0) return kKeyMigrateDown;
-    if (c.y >= g.own_row1) return kKeyMigrateUp;
+    if (c.y < g.own_row0 || c.y >= g.own_row1) return kKeyDrop;
     return static_cast<uint32_t>(c.y - g.row_base) * static_cast<uint32_t>(g.nx) + static_cast<uint32_t>(c.x);
 }
 

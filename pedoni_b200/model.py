@@ -43,7 +43,8 @@ class SocialForceModelCuda:
     `SocialForceModelGpu`), running on one B200."""
 
     def __init__(self, options, scenario, field, *, device: int = 0, math_mode: int = _capi.PEDONI_MATH_STRICT,
-                 capacity: int = 0, slab_rank: int = 0, slab_count: int = 1, stream: int = 0):
+                 capacity: int = 0, slab_rank: int = 0, slab_count: int = 1, stream: int = 0,
+                 halo_capacity: int = 0):
         """`PedestrianModel::new(&SimulatorOptions, &Scenario, &Field)` (mod.rs:14)."""
         self._lib = _capi.load()
         self._h = C.c_void_p()
@@ -70,6 +71,7 @@ class SocialForceModelCuda:
         cfg.math_mode = math_mode
         cfg.slab_rank, cfg.slab_count = slab_rank, slab_count
         cfg.stream = stream or None
+        cfg.halo_capacity = halo_capacity
         _capi.check(self._lib.pedoni_create(C.byref(cfg), C.byref(self._h)))
         self.n_maps = pots.shape[0]
 
@@ -190,6 +192,11 @@ class SocialForceModelCuda:
         buf = C.create_string_buffer(unique_id, _capi.PEDONI_COMM_ID_BYTES)
         _capi.check(self._lib.pedoni_comm_init(self._h, buf), self._h)
 
+    def halo_capacity(self) -> int:
+        h = C.c_uint32()
+        _capi.check(self._lib.pedoni_halo_capacity(self._h, C.byref(h)), self._h)
+        return h.value
+
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
             self._lib.pedoni_destroy(self._h)
@@ -200,6 +207,72 @@ class SocialForceModelCuda:
             self.close()
         except Exception:
             pass
+
+
+class SlabGroup:
+    """`slab_count` slab handles living in ONE process, exchanging ghost rows with the in-process
+    transport (pedoni_slab_exchange_local). Presents the same trait-shaped surface as a single
+    `SocialForceModelCuda`; outputs are the rank-order concatenation, which equals the whole-domain
+    order. One-process-per-GPU programs (bench.py under torchrun) use one handle + `comm_init` instead."""
+
+    def __init__(self, options, scenario, field, slab_count: int, *, devices=None, **kw):
+        devices = devices or [kw.pop("device", 0)] * slab_count
+        kw.pop("device", None)
+        self.slabs = [SocialForceModelCuda(options, scenario, field, device=devices[r], slab_rank=r,
+                                           slab_count=slab_count, **kw) for r in range(slab_count)]
+        self._lib = _capi.load()
+
+    def _exchange(self) -> None:
+        arr = (C.c_void_p * len(self.slabs))(*[s._h.value for s in self.slabs])
+        _capi.check(self._lib.pedoni_slab_exchange_local(arr, len(self.slabs)), self.slabs[0]._h)
+
+    def spawn_arrays(self, pos, dest, v0) -> None:  # replicated list; each slab keeps the rows it owns
+        for s in self.slabs:
+            s.spawn_arrays(pos, dest, v0)
+
+    def upload_state(self, pos, dest, vel, v0) -> None:
+        for s in self.slabs:
+            s.upload_state(pos, dest, vel, v0)
+
+    def rebuild(self) -> None:
+        for s in self.slabs:
+            s.rebuild()
+        self._exchange()
+
+    def step(self) -> None:
+        for s in self.slabs:
+            s.step()
+
+    update_states = step
+
+    def get_pedestrian_count(self) -> int:
+        return sum(s.get_pedestrian_count() for s in self.slabs)
+
+    def download(self, vel: bool = True, v0: bool = True):
+        parts = [s.download(vel=vel, v0=v0) for s in self.slabs]
+        cat = lambda k: None if parts[0][k] is None else np.concatenate([p[k] for p in parts])  # noqa: E731
+        return cat(0), cat(1), cat(2), cat(3)
+
+    def cell_table(self) -> np.ndarray:
+        """Whole-domain `neighbor_grid_indices` stitched from the slabs' owned rows."""
+        out, base = [np.zeros(1, np.uint32)], 0
+        for s in self.slabs:
+            t = s.cell_table().astype(np.uint64)
+            out.append((t[1:] + base).astype(np.uint32))
+            base += int(t[-1])
+        return np.concatenate(out)
+
+    def synchronize(self) -> None:
+        for s in self.slabs:
+            s.synchronize()
+
+    def counters(self):
+        c = [s.counters() for s in self.slabs]
+        return sum(x[0] for x in c), sum(x[1] for x in c)
+
+    def close(self) -> None:
+        for s in self.slabs:
+            s.close()
 
 
 def comm_unique_id() -> bytes:

@@ -1,0 +1,27 @@
+"""The real multi-GPU path: one process per GPU, ghost rows over NCCL send/recv (NVLink). Needs >= 2
+GPUs (`gpurun --gpus 2`); skipped on a single-GPU box, where tests/test_gpu_slabs.py covers the same
+slab logic with the in-process transport."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_nccl_slabs_equal_whole_domain(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           str(ROOT / "tests" / "nccl_slab_worker.py"), "400000", "25"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "NCCL-SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -94,8 +94,11 @@ def test_strict_single_step_is_bit_exact_or_1ulp(corridor):
     op, _, ov, _ = orc.get()
     mism = int((bits(cp) != bits(op)).sum() + (bits(cv) != bits(ov)).sum())
     print(f"strict: {mism} of {cp.size + cv.size} floats differ in bits; max |dpos| = {np.abs(cp - op).max():.3e}")
-    # exp is the only op not bit-identical to glibc by construction; allow a vanishing fraction
-    assert mism <= 0.001 * (cp.size + cv.size)
+    # exp is the only op not bit-identical by construction: the device rounds a correctly rounded fp64 exp
+    # once, glibc's expf (what Rust's f32::exp calls; FMA or non-FMA variant picked per CPU) is a 0.502-ulp
+    # routine. About 1 exp in 10^3 differs in the last bit, ~12 exps feed each velocity: allow 0.5 %
+    # of the outputs to differ, and only in the last bits.
+    assert mism <= 0.005 * (cp.size + cv.size)
     assert np.abs(cp - op).max() <= 1e-6 and np.abs(cv - ov).max() <= 1e-5
 
 

@@ -1,0 +1,139 @@
+"""Slab decomposition on ONE GPU: `slab_count` handles in one process exchanging ghost rows through the
+in-process transport must reproduce the whole-domain handle BIT FOR BIT (same kernels, same neighbor
+order, same summation order) — counts, cell table, order, positions and velocities — and therefore
+the oracle within the stated tolerance. The NCCL transport differs only in how the strips travel
+(tests/test_gpu_nccl_slabs.py, needs >= 2 GPUs)."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import bits
+from pedoni_b200 import (PEDONI_MATH_FAST, PEDONI_MATH_STRICT, PedoniError, SimulatorOptions, SlabGroup,
+                         SocialForceModelCuda)
+from pedoni_b200.synthetic import SyntheticCrowd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def corridor():
+    sc = helpers.corridor_scenario()
+    return sc, helpers.oracle_field(sc)
+
+
+def _assert_same(whole, slabs, what=""):
+    assert whole.get_pedestrian_count() == slabs.get_pedestrian_count(), what
+    wp, wd, wv, w0 = whole.download()
+    sp, sd, sv, s0 = slabs.download()
+    np.testing.assert_array_equal(wd, sd, err_msg=what)
+    np.testing.assert_array_equal(bits(wp), bits(sp), err_msg=what)
+    np.testing.assert_array_equal(bits(wv), bits(sv), err_msg=what)
+    np.testing.assert_array_equal(bits(w0), bits(s0), err_msg=what)
+
+
+@pytest.mark.parametrize("n_slabs", [2, 3, 4])
+@pytest.mark.parametrize("mode", [PEDONI_MATH_STRICT, PEDONI_MATH_FAST])
+def test_slabs_equal_whole_domain_bitwise(corridor, n_slabs, mode):
+    sc, field = corridor  # 22 x 43 neighbor grid: 4 slabs of 5-6 rows
+    opts = SimulatorOptions()
+    whole = SocialForceModelCuda(opts, sc, field, math_mode=mode)
+    slabs = SlabGroup(opts, sc, field, n_slabs, math_mode=mode)
+    pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=21, margin=3.5)
+    for m in (whole, slabs):
+        m.upload_state(pos, dest, vel, v0)
+    rng = np.random.default_rng(5)
+    for tick in range(25):
+        n = int(rng.poisson(15))  # spawn stream crossing slab boundaries: x fixed, y over the whole height
+        sp = np.stack([np.full(n, 6.0), rng.uniform(5, 25, n)], 1).astype(np.float32)
+        sd = np.ones(n, np.uint32)
+        s0 = np.clip(rng.normal(1.34, 0.26, n), 0.5, 2.2).astype(np.float32)
+        for m in (whole, slabs):
+            m.spawn_arrays(sp, sd, s0)
+            m.rebuild()
+        np.testing.assert_array_equal(whole.cell_table(), slabs.cell_table(), err_msg=f"tick {tick}")
+        _assert_same(whole, slabs, f"after rebuild, tick {tick}")
+        for m in (whole, slabs):
+            m.step()
+        _assert_same(whole, slabs, f"after step, tick {tick}")
+    assert whole.counters()[1] == slabs.counters()[1]  # ghost rows are integrated twice but counted once
+    whole.close()
+    slabs.close()
+
+
+def test_slabs_match_oracle(corridor):
+    sc, field = corridor
+    slabs = SlabGroup(SimulatorOptions(), sc, field, 3)
+    _, orc = helpers.make_pair(sc, field)
+    pos, dest, vel, v0 = helpers.random_crowd(2500, sc.field.size, seed=8, margin=4.0, speed=False)
+    slabs.spawn_arrays(pos, dest, v0)
+    slabs.rebuild()
+    orc.spawn(pos, dest, v0)
+    for _ in range(10):
+        np.testing.assert_array_equal(slabs.cell_table(), orc.indices())
+        slabs.step()
+        orc.update()
+        slabs.rebuild()
+        orc.spawn()
+    cp, cd, cv, _ = slabs.download()
+    op, od, ov, _ = orc.get()
+    np.testing.assert_array_equal(cd, od)
+    assert np.abs(cp - op).max() <= helpers.TOL_POS_ABS and np.abs(cv - ov).max() <= helpers.TOL_VEL_ABS
+
+
+def test_slabs_on_uniform_crowd_with_walkers_crossing_every_boundary():
+    """200k-agent synthetic crowd (BASELINE.json configs[4] at reduced N), 8 slabs, 30 ticks."""
+    crowd = SyntheticCrowd(n=200_000)
+    sc, field = crowd.scenario(), crowd.field()
+    pos, dest, vel, v0 = crowd.agents()
+    # make every agent walk along y so that each tick moves pedestrians across slab boundaries
+    vel[:, 1] = np.where(np.arange(len(vel)) % 2 == 0, 1.2, -1.2).astype(np.float32)
+    whole = SocialForceModelCuda(SimulatorOptions(), sc, field, math_mode=PEDONI_MATH_FAST, capacity=210_000)
+    slabs = SlabGroup(SimulatorOptions(), sc, field, 8, math_mode=PEDONI_MATH_FAST, capacity=30_000)
+    for m in (whole, slabs):
+        m.upload_state(pos, dest, vel, v0)
+        m.rebuild()
+    owned0 = [s.get_pedestrian_count() for s in slabs.slabs]
+    for tick in range(30):
+        for m in (whole, slabs):
+            m.step()
+            m.rebuild()
+    np.testing.assert_array_equal(whole.cell_table(), slabs.cell_table())
+    _assert_same(whole, slabs)
+    owned1 = [s.get_pedestrian_count() for s in slabs.slabs]
+    assert owned0 != owned1  # pedestrians did migrate between slabs
+    whole.close()
+    slabs.close()
+
+
+def test_halo_overflow_and_row_jump_are_reported(corridor):
+    sc, field = corridor
+    pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=3, margin=4.0)
+    small = SlabGroup(SimulatorOptions(), sc, field, 2, halo_capacity=16)
+    small.upload_state(pos, dest, vel, v0)
+    small.rebuild()
+    with pytest.raises(PedoniError) as e:
+        small.get_pedestrian_count()
+    assert "halo_capacity" in str(e.value)
+    small.close()
+
+    fast = SlabGroup(SimulatorOptions(), sc, field, 2)
+    v0_fast = np.full_like(v0, 40.0)  # 1.3 * 40 m/s * 0.1 s = 5.2 m per step > 2 rows
+    fast.upload_state(pos, dest, vel, v0_fast)
+    for _ in range(6):
+        fast.rebuild()
+        fast.step()
+    with pytest.raises(PedoniError) as e:
+        fast.get_pedestrian_count()
+    assert "two or more neighbor-grid rows" in str(e.value)
+    fast.close()
+
+
+def test_step_without_ghosts_is_refused(corridor):
+    sc, field = corridor
+    lone = SocialForceModelCuda(SimulatorOptions(), sc, field, slab_rank=0, slab_count=2)
+    lone.rebuild()
+    with pytest.raises(PedoniError):
+        lone.step()
+    lone.close()
+    with pytest.raises(PedoniError):  # 22 rows cannot give 12 slabs two rows each
+        SocialForceModelCuda(SimulatorOptions(), sc, field, slab_rank=0, slab_count=12)
