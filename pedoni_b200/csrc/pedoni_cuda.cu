@@ -564,7 +564,8 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
         if (c->halo_capacity) {
             m->halo_cap = c->halo_capacity;
         } else {  // 4x the two-row population of a uniformly filled slab
-            const uint64_t per_row = capacity / static_cast<uint32_t>(r1 - r0) + 1;
+            // (same on every rank: the message size must agree, so use the common floor of rows per slab)
+            const uint64_t per_row = capacity / static_cast<uint32_t>(m->grid.ny / m->slab_count) + 1;
             m->halo_cap = static_cast<uint32_t>(std::max<uint64_t>(4096, 8 * per_row));
         }
         m->halo_cap = (m->halo_cap + 255u) & ~255u;
@@ -816,7 +817,7 @@ int pedoni_rebuild(PedoniModel* m) {
     return rebuild_impl(m);
 }
 
-int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n) {
+static int slab_exchange_local_impl(PedoniModel* const* models, int32_t n) {
     if (!models || n < 1) return PEDONI_ERR_INVALID;
     for (int i = 0; i < n; ++i) {
         PedoniModel* m = models[i];
@@ -859,6 +860,16 @@ int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n) {
         CUDA_TRY(m, cudaGetLastError());
     }
     return PEDONI_OK;
+}
+
+int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n) {
+    int rc = slab_exchange_local_impl(models, n);
+    if (rc != PEDONI_OK) {  // a group call has no single handle: mirror the message into the handle-less slot
+        g_create_error = "invalid slab group";
+        for (int i = 0; models && i < n; ++i)
+            if (models[i] && !models[i]->last_error.empty()) g_create_error = models[i]->last_error;
+    }
+    return rc;
 }
 
 int pedoni_step(PedoniModel* m) {

@@ -224,7 +224,7 @@ class SlabGroup:
 
     def _exchange(self) -> None:
         arr = (C.c_void_p * len(self.slabs))(*[s._h.value for s in self.slabs])
-        _capi.check(self._lib.pedoni_slab_exchange_local(arr, len(self.slabs)), self.slabs[0]._h)
+        _capi.check(self._lib.pedoni_slab_exchange_local(arr, len(self.slabs)), None)
 
     def spawn_arrays(self, pos, dest, v0) -> None:  # replicated list; each slab keeps the rows it owns
         for s in self.slabs:

@@ -117,8 +117,10 @@ def test_halo_overflow_and_row_jump_are_reported(corridor):
     small.close()
 
     fast = SlabGroup(SimulatorOptions(), sc, field, 2)
-    v0_fast = np.full_like(v0, 40.0)  # 1.3 * 40 m/s * 0.1 s = 5.2 m per step > 2 rows
-    fast.upload_state(pos, dest, vel, v0_fast)
+    v0_fast = np.full_like(v0, 40.0)  # speed limit 1.3 * 40 m/s: a 30 m/s walker covers 3 m = 2 rows per step
+    vel_fast = vel.copy()
+    vel_fast[:, 1] = 30.0
+    fast.upload_state(pos, dest, vel_fast, v0_fast)
     for _ in range(6):
         fast.rebuild()
         fast.step()
