@@ -9,6 +9,25 @@
 // both. The epilogue also evaluates the next rebuild's cell key and despawn predicate
 // (neighbor_grid.rs:27-33, sfm.rs:69) on the just-integrated position, which is bit-identical to
 // evaluating it at the start of the next tick on the stored value.
+//
+// Kernel shape (one CTA = 128 consecutive agents of the cell-sorted arrays, one thread per agent):
+//   1. every thread loads its agent and the six cell-table entries bounding its three row ranges
+//      (rows cy-1, cy, cy+1; sfm.rs:117-127). Ranges are monotone in the agent index, so the CTA's
+//      union per row offset is ONE contiguous index window [first thread's start, last thread's end)
+//      — also across a row end, because consecutive rows are adjacent in the sorted arrays.
+//   2. the three windows (position and velocity) are staged in shared memory with coalesced loads:
+//      ~3.3 loads per agent instead of ~36 gathers per agent.
+//   3. SCAN: each thread walks its candidates in the tile (cheap: one LDS.64 and the 2 m cut-off test)
+//      and appends the in-range ones to a private list in shared memory, in index order.
+//   4. FORCE: each thread evaluates the Helbing-Molnar term for its list, in the same order as the
+//      reference sums it. Splitting scan from force keeps the expensive body converged: a warp runs
+//      max-over-lanes(in-range) ~ 18 heavy iterations instead of sum-over-rows max-over-lanes
+//      (candidates) ~ 29 with three fifths of the lanes idle (profiles/r01a_force_integrate_full.md:
+//      18.5 of 32 lanes active).
+//   5. steering + wall field samples (issued before the first barrier so their latency overlaps the
+//      staging), integration, key of the new position, coalesced stores.
+// CTAs whose windows exceed the tile (a cell holding hundreds of agents) read candidates from global
+// memory instead; that is a correctness path, not a fast path.
 #pragma once
 #include "grid_sort.cuh"
 
@@ -16,6 +35,12 @@ namespace pedoni {
 
 constexpr float kCosPhi = -0.17364817766693036f;  // sfm.rs:16
 constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0.y, b.x, b.y, |b|^2), w, h, pad
+
+constexpr int kForceThreads = 128;
+constexpr int kTileEntries = 768;  // agents per CTA tile: 3 windows of ~(128 + 2 cells) agents at any sane density
+constexpr int kListDepth = 48;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
+constexpr size_t kForceSmemBytes = 2 * sizeof(float2) * kTileEntries + sizeof(uint16_t) * kListDepth * kForceThreads;
+static_assert(kTileEntries <= 65536, "list entries are 16-bit tile indices");
 
 struct ForceParams {
     AgentArrays in;              // cell-sorted state (pre-integration)
@@ -33,42 +58,89 @@ struct ForceParams {
     int n_obstacles;
 };
 
-// sfm.rs:129-155. `self` is the agent being updated, `o` the other pedestrian.
+// ---- pair term, sfm.rs:129-155 ----------------------------------------------------------------------
+// (po, vo) = position and velocity of the other pedestrian; the caller has already applied the cut-off
+// `|d|^2 > 4 -> skip` (sfm.rs:133-135) and the self test (sfm.rs:130).
 template <Math M>
-__device__ __forceinline__ void pair_force(float2 pos, float2 e, float2 pos_o, float2 vel_o, float2& acc) {
-    using O = Ops<M>;
-    const float dx = O::sub(pos.x, pos_o.x), dy = O::sub(pos.y, pos_o.y);
-    const float d2 = O::add(O::mul(dx, dx), O::mul(dy, dy));
-    if (d2 > 4.0f) return;  // sfm.rs:133-135
+struct PairTerm;
 
-    const float dist = O::sqrt(d2);
-    const float rinv = O::rcp(dist);  // glam normalize = v * (1 / length)
-    const float dirx = O::mul(dx, rinv), diry = O::mul(dy, rinv);
+// Reference operation order, IEEE ops, no contraction.
+template <>
+struct PairTerm<Math::Strict> {
+    static __device__ __forceinline__ void add(float2 pos, float2 e, float2 po, float2 vo, float2& acc) {
+        using O = Ops<Math::Strict>;
+        const float dx = O::sub(pos.x, po.x), dy = O::sub(pos.y, po.y);
+        const float d2 = O::add(O::mul(dx, dx), O::mul(dy, dy));
+        const float dist = O::sqrt(d2);
+        const float rinv = O::rcp(dist);  // glam normalize = v * (1 / length)
+        const float dirx = O::mul(dx, rinv), diry = O::mul(dy, rinv);
 
-    const float t1x = O::sub(dx, O::mul(vel_o.x, 0.1f)), t1y = O::sub(dy, O::mul(vel_o.y, 0.1f));
-    const float t1len = O::sqrt(O::add(O::mul(t1x, t1x), O::mul(t1y, t1y)));
-    const float t2 = O::add(dist, t1len);
-    const float vl = O::mul(O::sqrt(O::add(O::mul(vel_o.x, vel_o.x), O::mul(vel_o.y, vel_o.y))), 0.1f);
-    const float b = O::mul(O::sqrt(O::sub(O::mul(t2, t2), O::mul(vl, vl))), 0.5f);
+        const float t1x = O::sub(dx, O::mul(vo.x, 0.1f)), t1y = O::sub(dy, O::mul(vo.y, 0.1f));
+        const float t1len = O::sqrt(O::add(O::mul(t1x, t1x), O::mul(t1y, t1y)));
+        const float t2 = O::add(dist, t1len);
+        const float vl = O::mul(O::sqrt(O::add(O::mul(vo.x, vo.x), O::mul(vo.y, vo.y))), 0.1f);
+        const float b = O::mul(O::sqrt(O::sub(O::mul(t2, t2), O::mul(vl, vl))), 0.5f);
 
-    // nabla_b = t2 * (direction + t1 / t1_length) / (4.0 * b)
-    const float sx = O::add(dirx, O::div(t1x, t1len)), sy = O::add(diry, O::div(t1y, t1len));
-    const float fb = O::mul(4.0f, b);
-    const float nbx = O::div(O::mul(t2, sx), fb), nby = O::div(O::mul(t2, sy), fb);
-    // force = 2.1 / 0.3 * exp(-b / 0.3) * nabla_b   (f32 constant 2.1/0.3 = 6.9999995)
-    const float coef = O::mul(2.1f / 0.3f, O::exp(O::div(-b, 0.3f)));
-    float fx = O::mul(coef, nbx), fy = O::mul(coef, nby);
+        // nabla_b = t2 * (direction + t1 / t1_length) / (4.0 * b)
+        const float sx = O::add(dirx, O::div(t1x, t1len)), sy = O::add(diry, O::div(t1y, t1len));
+        const float fb = O::mul(4.0f, b);
+        const float nbx = O::div(O::mul(t2, sx), fb), nby = O::div(O::mul(t2, sy), fb);
+        // force = 2.1 / 0.3 * exp(-b / 0.3) * nabla_b   (f32 constant 2.1/0.3 = 6.9999995)
+        const float coef = O::mul(2.1f / 0.3f, O::exp(O::div(-b, 0.3f)));
+        float fx = O::mul(coef, nbx), fy = O::mul(coef, nby);
 
-    // anisotropy, sfm.rs:150-152
-    const float lhs = O::add(O::mul(e.x, -fx), O::mul(e.y, -fy));
-    const float flen = O::sqrt(O::add(O::mul(fx, fx), O::mul(fy, fy)));
-    if (lhs < O::mul(flen, kCosPhi)) {
-        fx = O::mul(fx, 0.5f);
-        fy = O::mul(fy, 0.5f);
+        // anisotropy, sfm.rs:150-152
+        const float lhs = O::add(O::mul(e.x, -fx), O::mul(e.y, -fy));
+        const float flen = O::sqrt(O::add(O::mul(fx, fx), O::mul(fy, fy)));
+        if (lhs < O::mul(flen, kCosPhi)) {
+            fx = O::mul(fx, 0.5f);
+            fy = O::mul(fy, 0.5f);
+        }
+        acc.x = O::add(acc.x, fx);
+        acc.y = O::add(acc.y, fy);
     }
-    acc.x = O::add(acc.x, fx);
-    acc.y = O::add(acc.y, fy);
-}
+};
+
+// Same term with the algebra folded for the SFU/FMA pipes: 3 rsqrt + 1 ex2 and ~35 FP32 ops.
+//   2b = sqrt(q), q = t2^2 - |0.1 v_i|^2;  force = s * n with n = d/|d| + t1/|t1| and the positive scalar
+//   s = (2.1/0.3) exp(-b/0.3) t2 / (4b) = 3.5 * exp2(-(log2 e / 0.6) sqrt(q)) * t2 / sqrt(q).
+//   Anisotropy test e.(-f) < |f| cos(phi)  <=>  e.n > -cos(phi) |n|  <=>  e.n > 0 and (e.n)^2 > cos^2(phi) |n|^2
+//   (cos(phi) < 0), which needs no square root of |f|.
+template <>
+struct PairTerm<Math::Fast> {
+    static __device__ __forceinline__ float rsqrt(float a) {
+        float r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+        return r;
+    }
+    static __device__ __forceinline__ float ex2(float a) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+        return r;
+    }
+    static __device__ __forceinline__ void add(float2 pos, float2 e, float2 po, float2 vo, float2& acc) {
+        const float dx = pos.x - po.x, dy = pos.y - po.y;
+        const float d2 = fmaf(dy, dy, dx * dx);
+        const float rinv = rsqrt(d2);
+        const float wx = 0.1f * vo.x, wy = 0.1f * vo.y;
+        const float t1x = dx - wx, t1y = dy - wy;
+        const float t1sq = fmaf(t1y, t1y, t1x * t1x);
+        const float rt1 = rsqrt(t1sq);
+        const float t2 = fmaf(d2, rinv, t1sq * rt1);  // |d| + |t1|
+        const float q = fmaf(t2, t2, -fmaf(wy, wy, wx * wx));
+        const float rq = rsqrt(q);
+        constexpr float kC = -1.4426950408889634f / 0.6f;  // exp(-b/0.3), b = sqrt(q)/2, as exp2
+        constexpr float kLog2K = 1.8073549220576042f;      // log2(2.1 / 0.3 / 2)
+        float s = ex2(fmaf(q * rq, kC, kLog2K)) * (t2 * rq);
+        const float nx = fmaf(t1x, rt1, dx * rinv), ny = fmaf(t1y, rt1, dy * rinv);
+        const float en = fmaf(e.y, ny, e.x * nx);
+        const float n2 = fmaf(ny, ny, nx * nx);
+        constexpr float kCos2 = kCosPhi * kCosPhi;
+        if (en > 0.0f && en * en > kCos2 * n2) s *= 0.5f;
+        acc.x = fmaf(s, nx, acc.x);
+        acc.y = fmaf(s, ny, acc.y);
+    }
+};
 
 // util.rs:92-103 with b = l1 - l0 and |b|^2 precomputed on the host (same f32 ops, same values).
 template <Math M>
@@ -81,74 +153,210 @@ __device__ __forceinline__ float2 distance_from_edge(float2 p, const float* __re
     return make_float2(O::sub(ax, O::mul(t, bx)), O::sub(ay, O::mul(t, by)));
 }
 
+// Field gradient for the force terms. Strict: the reference's 8 (9) bilinear samples, bit for bit.
+// Fast: the same Sobel-of-bilinear evaluated separably on the 4x4 texel footprint with FMAs (~50 ops
+// instead of ~130); map borders take the strict path.
+template <Math M, bool WithCentre>
+__device__ __forceinline__ void field_gradient(const float* __restrict__ g, int ny, int nx, float2 q, float& gx,
+                                               float& gy, float& centre) {
+    if (M == Math::Fast) {
+        const float bx = floorf(q.x), by = floorf(q.y);
+        const int x0 = __float2int_rz(bx) - 1, y0 = __float2int_rz(by) - 1;
+        if (x0 >= 0 && y0 >= 0 && x0 + 3 < nx && y0 + 3 < ny) {
+            const float tx = q.x - bx, ty = q.y - by, sx = 1.0f - tx, sy = 1.0f - ty;
+            const float* base = g + static_cast<size_t>(y0) * nx + x0;
+            float t[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) t[r][c] = __ldg(base + static_cast<size_t>(r) * nx + c);
+            // u[r][c] = sum_b sum_a wy_b wx_a t[r+b][c+a]; gx = sum_r k_r (u[r][0] - u[r][2]), k = (1, 2, 1)
+            float h[4], v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) h[r] = fmaf(tx, t[r][1] - t[r][3], sx * (t[r][0] - t[r][2]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = fmaf(ty, t[1][c] - t[3][c], sy * (t[0][c] - t[2][c]));
+            const float hx0 = fmaf(ty, h[1], sy * h[0]), hx1 = fmaf(ty, h[2], sy * h[1]), hx2 = fmaf(ty, h[3], sy * h[2]);
+            const float vy0 = fmaf(tx, v[1], sx * v[0]), vy1 = fmaf(tx, v[2], sx * v[1]), vy2 = fmaf(tx, v[3], sx * v[2]);
+            gx = hx0 + 2.0f * hx1 + hx2;
+            gy = vy0 + 2.0f * vy1 + vy2;
+            if (WithCentre)
+                centre = fmaf(sy, fmaf(sx, t[1][1], tx * t[1][2]), ty * fmaf(sx, t[2][1], tx * t[2][2]));
+            else
+                centre = 0.0f;
+            return;
+        }
+    }
+    sobel_sample<WithCentre>(g, ny, nx, q, gx, gy, centre);
+}
+
+// Pair repulsion of one agent against its three candidate ranges held in the shared-memory tile
+// (sfm.rs:112-156). cur/stop are TILE indices. Rounds of SCAN (branch-free: one LDS.64, the cut-off
+// test in IEEE ops so the neighbor SET is exact in both modes, an unconditional 16-bit store and a
+// predicated advance) and FORCE (the converged heavy loop, two neighbours in flight for ILP, summed in
+// index order). A round scans at most as many candidates as the list has free slots, so any density
+// works; at 1 ped/m^2 one round covers everything.
+template <Math M>
+__device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const float2* __restrict__ tile_pos,
+                                                  const float2* __restrict__ tile_vel, uint16_t* __restrict__ list,
+                                                  uint32_t (&cur)[3], const uint32_t (&stop)[3], uint32_t self,
+                                                  float2& acc) {
+    uint16_t* const col = list + threadIdx.x;  // this thread's column: col[k * kForceThreads]
+    bool more;
+    do {
+        uint32_t cnt = 0;
+        more = false;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (more) continue;
+            uint32_t c = cur[d];
+            const uint32_t lim = min(stop[d], c + (static_cast<uint32_t>(kListDepth) - cnt));
+            for (; c < lim; ++c) {
+                const float2 po = tile_pos[c];
+                const float dx = S::sub(pos.x, po.x), dy = S::sub(pos.y, po.y);  // sfm.rs:131-135
+                bool ok = !(S::add(S::mul(dx, dx), S::mul(dy, dy)) > 4.0f);
+                if (d == 1) ok = ok && (c != self);  // sfm.rs:130
+                col[cnt * kForceThreads] = static_cast<uint16_t>(c);
+                cnt += ok ? 1u : 0u;
+            }
+            cur[d] = c;
+            more = c < stop[d];
+        }
+#pragma unroll 2
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t c = col[k * kForceThreads];
+            PairTerm<M>::add(pos, e, tile_pos[c], tile_vel[c], acc);
+        }
+    } while (more);
+}
+
+// Same, candidates read from global memory (CTAs whose windows do not fit the tile). Correctness path.
+template <Math M>
+__device__ __forceinline__ void pair_forces_global(float2 pos, float2 e, const float2* __restrict__ g_pos,
+                                                   const float2* __restrict__ g_vel, const uint32_t (&beg)[3],
+                                                   const uint32_t (&stop)[3], uint32_t self, float2& acc) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (uint32_t c = beg[d]; c < stop[d]; ++c) {
+            if (d == 1 && c == self) continue;
+            const float2 po = __ldg(g_pos + c);
+            const float dx = S::sub(pos.x, po.x), dy = S::sub(pos.y, po.y);
+            if (S::add(S::mul(dx, dx), S::mul(dy, dy)) > 4.0f) continue;
+            PairTerm<M>::add(pos, e, po, __ldg(g_vel + c), acc);
+        }
+    }
+}
+
 template <Math M, bool kDistanceMap>
-__global__ void __launch_bounds__(128) force_integrate_kernel(ForceParams p) {
+__global__ void __launch_bounds__(kForceThreads, 8) force_integrate_kernel(ForceParams p) {
     using O = Ops<M>;
-    extern __shared__ float s_edges[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tile_pos = reinterpret_cast<float2*>(smem_raw);
+    float2* tile_vel = tile_pos + kTileEntries;
+    uint16_t* list = reinterpret_cast<uint16_t*>(tile_vel + kTileEntries);
+    __shared__ uint32_t s_win[6];  // [begin, end) of the three staged index windows
 
     const uint32_t begin = p.d_range[0], end = p.d_range[1];
-    const uint32_t id = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t block_first = begin + blockIdx.x * kForceThreads;
+    if (block_first >= end) return;  // whole CTA beyond the live range (grids are sized from an upper bound)
+    const uint32_t id = block_first + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const uint32_t lo = max(begin, p.d_owned[0]), hi = min(end, p.d_owned[1]);
         if (hi > lo) atomicAdd(p.updates_total, static_cast<unsigned long long>(hi - lo));
     }
     const bool live = id < end;
-    if (kDistanceMap && !live) return;  // the segment variant needs every thread at its barriers
+    const uint32_t block_last = min(block_first + kForceThreads, end) - 1;
 
     float2 pos = make_float2(0.f, 0.f), vel = pos, e = pos, acc = pos;
     float v0 = 0.f;
     uint32_t dest = 0;
     int row = 0;
+    uint32_t r_beg[3] = {0, 0, 0}, r_end[3] = {0, 0, 0};  // candidate index ranges, rows cy-1, cy, cy+1
     if (live) {
         pos = p.in.pos[id];
         vel = p.in.vel[id];
         v0 = p.in.v0[id];
         dest = p.in.dest[id];
 
-        // ---- steering (sfm.rs:106-109; field.rs:248-252)
-        const float2 q = field_coord(pos, p.field.unit);
-        {
-            float gx, gy, unused;
-            // dest < n_maps is guaranteed by the rebuild that admitted this agent (sort_key).
-            sobel_sample<false>(p.field.potential_maps + static_cast<size_t>(dest) * p.field.fy * p.field.fx,
-                                p.field.fy, p.field.fx, q, gx, gy, unused);
-            const float rlen = O::rcp(O::sqrt(O::add(O::mul(gx, gx), O::mul(gy, gy))));
-            e = make_float2(O::mul(gx, rlen), O::mul(gy, rlen));
-            acc.x = O::add(acc.x, O::div(O::sub(O::mul(e.x, v0), vel.x), 0.5f));
-            acc.y = O::add(acc.y, O::div(O::sub(O::mul(e.y, v0), vel.y), 0.5f));
-        }
-
-        // ---- pair repulsion (sfm.rs:112-156)
-        {
-            const int2 c = cell_of(pos, p.grid.unit);
-            row = c.y;
-            // Reference clamps to the grid; the local table may start at row_base (slabs) and always
-            // holds every row a live agent can reach (its own rows plus one halo row each side).
-            const int ly = c.y - p.grid.row_base;
-            const int y_start = max(ly - 1, 0), y_end = min(ly + 1, p.grid.table_rows - 1);
-            const int x_start = min(max(c.x - 1, 0), p.grid.nx - 1), x_end = max(min(c.x + 1, p.grid.nx - 1), 0);
-            for (int y = y_start; y <= y_end; ++y) {
-                const uint32_t* row = p.cell_start + static_cast<size_t>(y) * p.grid.nx;
-                const uint32_t i_start = __ldg(row + x_start), i_end = __ldg(row + x_end + 1);
-                for (uint32_t i = i_start; i < i_end; ++i) {
-                    if (i != id) pair_force<M>(pos, e, __ldg(p.in.pos + i), __ldg(p.in.vel + i), acc);
-                }
+        // ---- neighbour ranges (sfm.rs:113-127). The reference clamps to the grid; the local table may
+        // start at row_base (slabs) and always holds every row a live agent can reach.
+        const int2 c = cell_of(pos, p.grid.unit);
+        row = c.y;
+        const int ly = c.y - p.grid.row_base;
+        const int x_start = min(max(c.x - 1, 0), p.grid.nx - 1), x_end = max(min(c.x + 1, p.grid.nx - 1), 0);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int y = ly + d - 1;
+            if (y >= 0 && y < p.grid.table_rows) {
+                const uint32_t* rowp = p.cell_start + static_cast<size_t>(y) * p.grid.nx;
+                r_beg[d] = __ldg(rowp + x_start);
+                r_end[d] = __ldg(rowp + x_end + 1);
+            } else {  // off the grid: an empty range, placed so that the windows stay monotone
+                const size_t at = (y < 0) ? 0 : static_cast<size_t>(p.grid.table_rows) * p.grid.nx;
+                r_beg[d] = r_end[d] = __ldg(p.cell_start + at);
             }
         }
+        if (id == block_first) s_win[0] = r_beg[0], s_win[2] = r_beg[1], s_win[4] = r_beg[2];
+        if (id == block_last) s_win[1] = r_end[0], s_win[3] = r_end[1], s_win[5] = r_end[2];
+    }
 
-        // ---- walls, distance-map variant (sfm.rs:188-192; field.rs:242-245,255-258)
+    // ---- steering (sfm.rs:106-109; field.rs:248-252) and walls from the distance map (sfm.rs:188-192;
+    // field.rs:242-245,255-258). Issued before the barrier: their gathers overlap the tile staging.
+    float2 wall = make_float2(0.f, 0.f);
+    if (live) {
+        const float2 q = field_coord(pos, p.field);
+        float gx, gy, unused;
+        // dest < n_maps is guaranteed by the rebuild that admitted this agent (sort_key).
+        field_gradient<M, false>(p.field.potential_maps + static_cast<size_t>(dest) * p.field.fy * p.field.fx,
+                                 p.field.fy, p.field.fx, q, gx, gy, unused);
+        const float rlen = O::rcp(O::sqrt(O::add(O::mul(gx, gx), O::mul(gy, gy))));
+        e = make_float2(O::mul(gx, rlen), O::mul(gy, rlen));
+        acc.x = O::add(acc.x, O::div(O::sub(O::mul(e.x, v0), vel.x), 0.5f));
+        acc.y = O::add(acc.y, O::div(O::sub(O::mul(e.y, v0), vel.y), 0.5f));
         if (kDistanceMap) {
-            float gx, gy, distance;
-            sobel_sample<true>(p.field.distance_map, p.field.fy, p.field.fx, q, gx, gy, distance);
-            const float rlen = O::rcp(O::sqrt(O::add(O::mul(gx, gx), O::mul(gy, gy))));
+            float dgx, dgy, distance;
+            field_gradient<M, true>(p.field.distance_map, p.field.fy, p.field.fx, q, dgx, dgy, distance);
+            const float rl = O::rcp(O::sqrt(O::add(O::mul(dgx, dgx), O::mul(dgy, dgy))));
             const float coef = O::mul(10.0f * 0.2f, O::exp(O::div(-distance, 0.2f)));
-            acc.x = O::add(acc.x, O::mul(coef, -O::mul(gx, rlen)));
-            acc.y = O::add(acc.y, O::mul(coef, -O::mul(gy, rlen)));
+            wall = make_float2(O::mul(coef, -O::mul(dgx, rl)), O::mul(coef, -O::mul(dgy, rl)));
+        }
+    }
+    __syncthreads();
+
+    // ---- stage the three windows: tile = [w0 | w1 | w2]
+    const uint32_t w0 = s_win[0], w1 = s_win[2], w2 = s_win[4];
+    const uint32_t n0 = s_win[1] - w0, n1 = s_win[3] - w1, n2 = s_win[5] - w2;
+    const bool tiled = s_win[1] >= w0 && s_win[3] >= w1 && s_win[5] >= w2 &&
+                       (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries);
+    if (tiled) {
+        for (uint32_t k = threadIdx.x; k < n0 + n1 + n2; k += kForceThreads) {
+            const uint32_t i = k < n0 ? w0 + k : (k < n0 + n1 ? w1 + (k - n0) : w2 + (k - n0 - n1));
+            tile_pos[k] = __ldg(p.in.pos + i);
+            tile_vel[k] = __ldg(p.in.vel + i);
+        }
+    }
+    __syncthreads();
+
+    // ---- pair repulsion (sfm.rs:112-156)
+    if (live) {
+        if (tiled) {
+            // candidate c of row offset d sits at tile index c - off[d]
+            const uint32_t off[3] = {w0, w1 - n0, w2 - n0 - n1};
+            uint32_t cur[3] = {r_beg[0] - off[0], r_beg[1] - off[1], r_beg[2] - off[2]};
+            const uint32_t stop[3] = {r_end[0] - off[0], r_end[1] - off[1], r_end[2] - off[2]};
+            pair_forces_tiled<M>(pos, e, tile_pos, tile_vel, list, cur, stop, id - off[1], acc);
+        } else {
+            pair_forces_global<M>(pos, e, p.in.pos, p.in.vel, r_beg, r_end, id, acc);
+        }
+        if (kDistanceMap) {
+            acc.x = O::add(acc.x, wall.x);
+            acc.y = O::add(acc.y, wall.y);
         }
     }
 
-    // ---- walls, segment variant (sfm.rs:193-237): obstacles staged through shared memory
+    // ---- walls, segment variant (sfm.rs:193-237): obstacles staged through shared memory (the tile is free now)
     if (!kDistanceMap) {
+        float* s_edges = reinterpret_cast<float*>(smem_raw);
         constexpr int kChunk = 64;  // obstacles per stage: 64 * 24 * 4 B = 6 KB
         for (int o0 = 0; o0 < p.n_obstacles; o0 += kChunk) {
             const int n = min(kChunk, p.n_obstacles - o0);
@@ -186,8 +394,8 @@ __global__ void __launch_bounds__(128) force_integrate_kernel(ForceParams p) {
                 acc.y = O::add(acc.y, O::mul(coef, O::mul(md.y, rlen)));
             }
         }
-        if (!live) return;
     }
+    if (!live) return;
 
     // ---- integration (sfm.rs:243-254), dt = 0.1
     float2 vn = make_float2(O::add(vel.x, O::mul(acc.x, 0.1f)), O::add(vel.y, O::mul(acc.y, 0.1f)));

@@ -343,12 +343,12 @@ SortInput make_sort_input(PedoniModel* m) {
 
 template <Math M, bool D>
 void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem, cudaStream_t s) {
-    force_integrate_kernel<M, D><<<blocks, 128, smem, s>>>(p);
+    force_integrate_kernel<M, D><<<blocks, kForceThreads, smem, s>>>(p);
     m->launches += 1;
 }
 
 void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream_t s) {
-    const uint32_t blocks = div_up(count_upper, 128);
+    const uint32_t blocks = div_up(count_upper, kForceThreads);
     if (blocks == 0) return;
     ForceParams p{};
     p.in = m->buf[m->cur];
@@ -364,7 +364,7 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     p.updates_total = m->d_updates;
     p.obstacle_edges = m->d_edges;
     p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
-    const size_t smem = m->use_distance_map ? 0 : sizeof(float) * 64 * kEdgeFloats;
+    const size_t smem = kForceSmemBytes;  // tile + neighbour lists; the segment-wall variant reuses the tile
     ScopedTimer t(m, kForce, s, count_upper);
     if (m->math_mode == PEDONI_MATH_STRICT) {
         if (m->use_distance_map)
@@ -582,6 +582,11 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
 
     // Field (field.rs:194-205)
     m->field.unit = c->field_grid_unit;
+    {
+        int exp2 = 0;  // unit = 0.5 * 2^exp2 exactly <=> power of two; then 1/unit is exact as well
+        m->field.inv_unit = (std::frexp(c->field_grid_unit, &exp2) == 0.5f && exp2 > -120 && exp2 < 120)
+                                ? 1.0f / c->field_grid_unit : 0.0f;
+    }
     m->field.fy = c->field_ny;
     m->field.fx = c->field_nx;
     m->field.n_maps = c->n_potential_maps;

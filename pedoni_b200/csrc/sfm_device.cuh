@@ -59,6 +59,7 @@ using S = Ops<Math::Strict>;
 // ------------------------------------------------------------------------------------------------
 struct FieldView {
     float unit;
+    float inv_unit;  // 1 / unit when unit is a power of two (then x * inv_unit == x / unit bit for bit), else 0
     int fy, fx;
     int n_maps;
     const float* __restrict__ distance_map;
@@ -101,13 +102,15 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ g, int ny, i
 }
 
 // `position / unit - 0.5` (field.rs:236,243,250,256): true divide, then subtract.
-__device__ __forceinline__ float2 field_coord(float2 pos, float unit) {
-    return make_float2(S::sub(S::div(pos.x, unit), 0.5f), S::sub(S::div(pos.y, unit), 0.5f));
+__device__ __forceinline__ float2 field_coord(float2 pos, const FieldView& f) {
+    if (f.inv_unit != 0.0f)  // default unit 0.25: scaling by a power of two is exact, no IEEE divide needed
+        return make_float2(S::sub(S::mul(pos.x, f.inv_unit), 0.5f), S::sub(S::mul(pos.y, f.inv_unit), 0.5f));
+    return make_float2(S::sub(S::div(pos.x, f.unit), 0.5f), S::sub(S::div(pos.y, f.unit), 0.5f));
 }
 
 // field.rs:235-239
 __device__ __forceinline__ float get_potential(const FieldView& f, uint32_t waypoint, float2 pos) {
-    float2 q = field_coord(pos, f.unit);
+    float2 q = field_coord(pos, f);
     return bilinear(f.potential_maps + static_cast<size_t>(waypoint) * f.fy * f.fx, f.fy, f.fx, q.x, q.y);
 }
 
