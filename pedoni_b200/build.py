@@ -38,19 +38,21 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, extra=()) -> Path:
+    """`out` / `extra` build a tuning variant elsewhere (scripts/sweep_force.py); the default is the product."""
+    if out is None and not force and not needs_build():
         return OUT
+    out = out or OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(nvcc).exists():
         raise RuntimeError("nvcc not found; libpedoni_cuda.so cannot be built (there is no CPU fallback)")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(OUT), *map(str, sources()), "-lgomp", "-ldl"]
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(out), *map(str, sources()), "-lgomp", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     env = dict(os.environ)
     subprocess.run(cmd, check=True, env=env)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

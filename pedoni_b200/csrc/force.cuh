@@ -10,23 +10,25 @@
 // (neighbor_grid.rs:27-33, sfm.rs:69) on the just-integrated position, which is bit-identical to
 // evaluating it at the start of the next tick on the stored value.
 //
-// Kernel shape (one CTA = 128 consecutive agents of the cell-sorted arrays, one thread per agent):
-//   1. every thread loads its agent and the six cell-table entries bounding its three row ranges
-//      (rows cy-1, cy, cy+1; sfm.rs:117-127). Ranges are monotone in the agent index, so the CTA's
-//      union per row offset is ONE contiguous index window [first thread's start, last thread's end)
-//      — also across a row end, because consecutive rows are adjacent in the sorted arrays.
-//   2. the three windows (position and velocity) are staged in shared memory with coalesced loads:
-//      ~3.3 loads per agent instead of ~36 gathers per agent.
-//   3. SCAN: each thread walks its candidates in the tile (cheap: one LDS.64 and the 2 m cut-off test)
-//      and appends the in-range ones to a private list in shared memory, in index order.
-//   4. FORCE: each thread evaluates the Helbing-Molnar term for its list, in the same order as the
+// Kernel shape (one WARP = 32 consecutive agents of the cell-sorted arrays, one thread per agent;
+// warps are autonomous: no block-wide barrier on the distance-map path):
+//   1. every lane loads its agent and the six cell-table entries bounding its three row ranges
+//      (rows cy-1, cy, cy+1; sfm.rs:117-127). Ranges are monotone in the agent index, so the warp's
+//      union per row offset is ONE contiguous index window [first lane's start, last lane's end)
+//      — also across a row end, because consecutive rows are adjacent in the sorted arrays. The bounds
+//      travel by warp shuffle.
+//   2. the three windows (position and velocity) are staged in the warp's slice of shared memory with
+//      cp.async (LDGSTS: no registers, no waiting) — ~4 coalesced 8-byte copies per agent instead of
+//      ~36 gathers — while the lanes issue and evaluate the steering / wall field samples.
+//   3. SCAN: each lane walks its candidates in the tile (one LDS.64 and the 2 m cut-off test, branch
+//      free) and appends the in-range ones to a private list in shared memory, in index order.
+//   4. FORCE: each lane evaluates the Helbing-Molnar term for its list, in the same order as the
 //      reference sums it. Splitting scan from force keeps the expensive body converged: a warp runs
 //      max-over-lanes(in-range) ~ 18 heavy iterations instead of sum-over-rows max-over-lanes
 //      (candidates) ~ 29 with three fifths of the lanes idle (profiles/r01a_force_integrate_full.md:
 //      18.5 of 32 lanes active).
-//   5. steering + wall field samples (issued before the first barrier so their latency overlaps the
-//      staging), integration, key of the new position, coalesced stores.
-// CTAs whose windows exceed the tile (a cell holding hundreds of agents) read candidates from global
+//   5. integration, key of the new position, coalesced stores.
+// Warps whose windows exceed their tile (a cell holding ~100 agents) read candidates from global
 // memory instead; that is a correctness path, not a fast path.
 #pragma once
 #include "grid_sort.cuh"
@@ -36,11 +38,27 @@ namespace pedoni {
 constexpr float kCosPhi = -0.17364817766693036f;  // sfm.rs:16
 constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0.y, b.x, b.y, |b|^2), w, h, pad
 
-constexpr int kForceThreads = 128;
-constexpr int kTileEntries = 768;  // agents per CTA tile: 3 windows of ~(128 + 2 cells) agents at any sane density
-constexpr int kListDepth = 48;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
-constexpr size_t kForceSmemBytes = 2 * sizeof(float2) * kTileEntries + sizeof(uint16_t) * kListDepth * kForceThreads;
+// Tunables (overridable at build time for sweeps: scripts/sweep_force.sh).
+#ifndef PEDONI_FORCE_THREADS
+#define PEDONI_FORCE_THREADS 128
+#endif
+#ifndef PEDONI_FORCE_MIN_BLOCKS
+#define PEDONI_FORCE_MIN_BLOCKS 9
+#endif
+#ifndef PEDONI_TILE_ENTRIES
+#define PEDONI_TILE_ENTRIES 192
+#endif
+#ifndef PEDONI_LIST_DEPTH
+#define PEDONI_LIST_DEPTH 32
+#endif
+constexpr int kForceThreads = PEDONI_FORCE_THREADS;
+constexpr int kForceWarps = kForceThreads / 32;
+constexpr int kTileEntries = PEDONI_TILE_ENTRIES;  // agents per WARP tile: 3 windows of ~(32 + 2 cells) agents (~108 at 1 ped/m^2)
+constexpr int kListDepth = PEDONI_LIST_DEPTH;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
+constexpr size_t kWarpSmemBytes = 2 * sizeof(float2) * kTileEntries + sizeof(uint16_t) * kListDepth * 32;
+constexpr size_t kForceSmemBytes = kWarpSmemBytes * kForceWarps;
 static_assert(kTileEntries <= 65536, "list entries are 16-bit tile indices");
+static_assert(kWarpSmemBytes % 16 == 0, "warp slices stay 16-byte aligned");
 
 struct ForceParams {
     AgentArrays in;              // cell-sorted state (pre-integration)
@@ -201,7 +219,7 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
                                                   const float2* __restrict__ tile_vel, uint16_t* __restrict__ list,
                                                   uint32_t (&cur)[3], const uint32_t (&stop)[3], uint32_t self,
                                                   float2& acc) {
-    uint16_t* const col = list + threadIdx.x;  // this thread's column: col[k * kForceThreads]
+    uint16_t* const col = list + (threadIdx.x & 31);  // this lane's column: col[k * 32]
     bool more;
     do {
         uint32_t cnt = 0;
@@ -216,7 +234,7 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
                 const float dx = S::sub(pos.x, po.x), dy = S::sub(pos.y, po.y);  // sfm.rs:131-135
                 bool ok = !(S::add(S::mul(dx, dx), S::mul(dy, dy)) > 4.0f);
                 if (d == 1) ok = ok && (c != self);  // sfm.rs:130
-                col[cnt * kForceThreads] = static_cast<uint16_t>(c);
+                col[cnt * 32] = static_cast<uint16_t>(c);
                 cnt += ok ? 1u : 0u;
             }
             cur[d] = c;
@@ -224,7 +242,7 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
         }
 #pragma unroll 2
         for (uint32_t k = 0; k < cnt; ++k) {
-            const uint32_t c = col[k * kForceThreads];
+            const uint32_t c = col[k * 32];
             PairTerm<M>::add(pos, e, tile_pos[c], tile_vel[c], acc);
         }
     } while (more);
@@ -247,25 +265,34 @@ __device__ __forceinline__ void pair_forces_global(float2 pos, float2 e, const f
     }
 }
 
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <Math M, bool kDistanceMap>
-__global__ void __launch_bounds__(kForceThreads, 8) force_integrate_kernel(ForceParams p) {
+__global__ void __launch_bounds__(kForceThreads, PEDONI_FORCE_MIN_BLOCKS) force_integrate_kernel(ForceParams p) {
     using O = Ops<M>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tile_pos = reinterpret_cast<float2*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile_pos = reinterpret_cast<float2*>(smem_raw + kWarpSmemBytes * warp);
     float2* tile_vel = tile_pos + kTileEntries;
     uint16_t* list = reinterpret_cast<uint16_t*>(tile_vel + kTileEntries);
-    __shared__ uint32_t s_win[6];  // [begin, end) of the three staged index windows
 
     const uint32_t begin = p.d_range[0], end = p.d_range[1];
     const uint32_t block_first = begin + blockIdx.x * kForceThreads;
     if (block_first >= end) return;  // whole CTA beyond the live range (grids are sized from an upper bound)
-    const uint32_t id = block_first + threadIdx.x;
+    const uint32_t warp_first = block_first + warp * 32;
+    // The segment-wall variant has block-wide barriers further down: its idle warps must stay.
+    if (kDistanceMap && warp_first >= end) return;
+    const uint32_t id = warp_first + lane;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const uint32_t lo = max(begin, p.d_owned[0]), hi = min(end, p.d_owned[1]);
         if (hi > lo) atomicAdd(p.updates_total, static_cast<unsigned long long>(hi - lo));
     }
     const bool live = id < end;
-    const uint32_t block_last = min(block_first + kForceThreads, end) - 1;
+    const int last_lane = warp_first < end ? static_cast<int>(min(32u, end - warp_first)) - 1 : 0;
 
     float2 pos = make_float2(0.f, 0.f), vel = pos, e = pos, acc = pos;
     float v0 = 0.f;
@@ -296,12 +323,26 @@ __global__ void __launch_bounds__(kForceThreads, 8) force_integrate_kernel(Force
                 r_beg[d] = r_end[d] = __ldg(p.cell_start + at);
             }
         }
-        if (id == block_first) s_win[0] = r_beg[0], s_win[2] = r_beg[1], s_win[4] = r_beg[2];
-        if (id == block_last) s_win[1] = r_end[0], s_win[3] = r_end[1], s_win[5] = r_end[2];
+    }
+
+    // ---- the warp's three index windows -> its tile [w0 | w1 | w2], staged asynchronously
+    const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, r_beg[0], 0), w1 = __shfl_sync(0xFFFFFFFFu, r_beg[1], 0),
+                   w2 = __shfl_sync(0xFFFFFFFFu, r_beg[2], 0);
+    const uint32_t e0 = __shfl_sync(0xFFFFFFFFu, r_end[0], last_lane), e1 = __shfl_sync(0xFFFFFFFFu, r_end[1], last_lane),
+                   e2 = __shfl_sync(0xFFFFFFFFu, r_end[2], last_lane);
+    const uint32_t n0 = e0 - w0, n1 = e1 - w1, n2 = e2 - w2;
+    const bool tiled = e0 >= w0 && e1 >= w1 && e2 >= w2 &&
+                       (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries);
+    if (tiled) {
+        for (uint32_t k = lane; k < n0 + n1 + n2; k += 32) {
+            const uint32_t i = k < n0 ? w0 + k : (k < n0 + n1 ? w1 + (k - n0) : w2 + (k - n0 - n1));
+            cp_async_8(tile_pos + k, p.in.pos + i);
+            cp_async_8(tile_vel + k, p.in.vel + i);
+        }
     }
 
     // ---- steering (sfm.rs:106-109; field.rs:248-252) and walls from the distance map (sfm.rs:188-192;
-    // field.rs:242-245,255-258). Issued before the barrier: their gathers overlap the tile staging.
+    // field.rs:242-245,255-258), evaluated while the tile copies are in flight.
     float2 wall = make_float2(0.f, 0.f);
     if (live) {
         const float2 q = field_coord(pos, p.field);
@@ -321,21 +362,8 @@ __global__ void __launch_bounds__(kForceThreads, 8) force_integrate_kernel(Force
             wall = make_float2(O::mul(coef, -O::mul(dgx, rl)), O::mul(coef, -O::mul(dgy, rl)));
         }
     }
-    __syncthreads();
-
-    // ---- stage the three windows: tile = [w0 | w1 | w2]
-    const uint32_t w0 = s_win[0], w1 = s_win[2], w2 = s_win[4];
-    const uint32_t n0 = s_win[1] - w0, n1 = s_win[3] - w1, n2 = s_win[5] - w2;
-    const bool tiled = s_win[1] >= w0 && s_win[3] >= w1 && s_win[5] >= w2 &&
-                       (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries);
-    if (tiled) {
-        for (uint32_t k = threadIdx.x; k < n0 + n1 + n2; k += kForceThreads) {
-            const uint32_t i = k < n0 ? w0 + k : (k < n0 + n1 ? w1 + (k - n0) : w2 + (k - n0 - n1));
-            tile_pos[k] = __ldg(p.in.pos + i);
-            tile_vel[k] = __ldg(p.in.vel + i);
-        }
-    }
-    __syncthreads();
+    cp_async_wait_all();
+    __syncwarp();
 
     // ---- pair repulsion (sfm.rs:112-156)
     if (live) {
