@@ -51,11 +51,18 @@ constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0
 #ifndef PEDONI_LIST_DEPTH
 #define PEDONI_LIST_DEPTH 32
 #endif
+#ifndef PEDONI_FAST_FIELD
+#define PEDONI_FAST_FIELD 1  // 0: PEDONI_MATH_FAST keeps the reference-order field gradient (experiments)
+#endif
+#ifndef PEDONI_FAST_PAIR
+#define PEDONI_FAST_PAIR 1   // 0: PEDONI_MATH_FAST keeps the reference-order pair term (experiments)
+#endif
 constexpr int kForceThreads = PEDONI_FORCE_THREADS;
 constexpr int kForceWarps = kForceThreads / 32;
 constexpr int kTileEntries = PEDONI_TILE_ENTRIES;  // agents per WARP tile: 3 windows of ~(32 + 2 cells) agents (~108 at 1 ped/m^2)
 constexpr int kListDepth = PEDONI_LIST_DEPTH;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
-constexpr size_t kWarpSmemBytes = 2 * sizeof(float2) * kTileEntries + sizeof(uint16_t) * kListDepth * 32;
+constexpr int kTileAlloc = kTileEntries + 2;  // +1 spare slot for the scan's read-ahead, +1 keeps 16-byte alignment
+constexpr size_t kWarpSmemBytes = 2 * sizeof(float2) * kTileAlloc + sizeof(uint16_t) * kListDepth * 32;
 constexpr size_t kForceSmemBytes = kWarpSmemBytes * kForceWarps;
 static_assert(kTileEntries <= 65536, "list entries are 16-bit tile indices");
 static_assert(kWarpSmemBytes % 16 == 0, "warp slices stay 16-byte aligned");
@@ -173,21 +180,37 @@ __device__ __forceinline__ float2 distance_from_edge(float2 p, const float* __re
 
 // Field gradient for the force terms. Strict: the reference's 8 (9) bilinear samples, bit for bit.
 // Fast: the same Sobel-of-bilinear evaluated separably on the 4x4 texel footprint with FMAs (~50 ops
-// instead of ~130); map borders take the strict path.
+// instead of ~130). Two cases keep the reference's operation order even in fast mode:
+//   - map borders (out-of-bounds taps read 1e12, util.rs:45);
+//   - footprints holding through-wall values (>= 1e5 * unit; obstacle cells cost 1e6 * unit,
+//     field.rs:102): there the reference's sums of ~2.5e5-sized samples cancel catastrophically and
+//     the rounding noise IS the behaviour — pedestrians in sealed pockets random-walk on it. The
+//     separable form is more accurate, and measurably changes evacuation.toml's statistics
+//     (40 %-evacuation time 31.6 +- 1.8 s instead of the reference order's 22.6 +- 1.2 s over 20
+//     separable form is more accurate there, so it is only used where that noise is below 0.1 % of a texel;
+//   - (near-)vanishing gradients, where the reference yields either noise or an exact zero (-> NaN ->
+//     the pedestrian disappears). Without this guard evacuation.toml, whose spawn lines lie exactly on
+//     corridor mid-lines, kept 13 pedestrians the reference loses in the first tick (40 %-evacuation
+//     time 31.6 +- 1.8 s instead of 22.6 +- 1.2 s over 20 seeds; scripts/exp_fast_stats.py).
 template <Math M, bool WithCentre>
-__device__ __forceinline__ void field_gradient(const float* __restrict__ g, int ny, int nx, float2 q, float& gx,
-                                               float& gy, float& centre) {
-    if (M == Math::Fast) {
+__device__ __forceinline__ void field_gradient(const float* __restrict__ g, int ny, int nx, float2 q, float noise_limit,
+                                               float flat_limit2, float& gx, float& gy, float& centre) {
+    if (M == Math::Fast && PEDONI_FAST_FIELD) {
         const float bx = floorf(q.x), by = floorf(q.y);
         const int x0 = __float2int_rz(bx) - 1, y0 = __float2int_rz(by) - 1;
         if (x0 >= 0 && y0 >= 0 && x0 + 3 < nx && y0 + 3 < ny) {
             const float tx = q.x - bx, ty = q.y - by, sx = 1.0f - tx, sy = 1.0f - ty;
             const float* base = g + static_cast<size_t>(y0) * nx + x0;
             float t[4][4];
+            float big = 0.0f;
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) t[r][c] = __ldg(base + static_cast<size_t>(r) * nx + c);
+                for (int c = 0; c < 4; ++c) {
+                    t[r][c] = __ldg(base + static_cast<size_t>(r) * nx + c);
+                    big = fmaxf(big, t[r][c]);
+                }
+            if (big < noise_limit) {
             // u[r][c] = sum_b sum_a wy_b wx_a t[r+b][c+a]; gx = sum_r k_r (u[r][0] - u[r][2]), k = (1, 2, 1)
             float h[4], v[4];
 #pragma unroll
@@ -202,7 +225,13 @@ __device__ __forceinline__ void field_gradient(const float* __restrict__ g, int 
                 centre = fmaf(sy, fmaf(sx, t[1][1], tx * t[1][2]), ty * fmaf(sx, t[2][1], tx * t[2][2]));
             else
                 centre = 0.0f;
-            return;
+            // A (near-)vanishing gradient — the mid-line of a corridor in the distance map, a spawn line
+            // placed exactly on it (evacuation.toml) — is where the reference's result is either rounding
+            // noise or exactly (0, 0), and (0, 0) normalises to NaN and removes the pedestrian at the next
+            // rebuild (sfm.rs:108,190). Only the reference's own operation order
+            // reproduces which of the two happens, so such samples are redone below.
+            if (fmaf(gx, gx, gy * gy) > flat_limit2) return;
+            }
         }
     }
     sobel_sample<WithCentre>(g, ny, nx, q, gx, gy, centre);
@@ -229,13 +258,19 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
             if (more) continue;
             uint32_t c = cur[d];
             const uint32_t lim = min(stop[d], c + (static_cast<uint32_t>(kListDepth) - cnt));
+            // Rows hold ~6 candidates: keep the loop rolled (an unrolled-by-4 body with its remainder
+            // ladder costs more than it hides) and software-pipeline the tile read instead. Reading one
+            // entry past `lim` stays inside the warp's slice (the tile has a spare slot).
+            float2 po = tile_pos[c];
+#pragma unroll 1
             for (; c < lim; ++c) {
-                const float2 po = tile_pos[c];
+                const float2 nxt = tile_pos[c + 1];
                 const float dx = S::sub(pos.x, po.x), dy = S::sub(pos.y, po.y);  // sfm.rs:131-135
                 bool ok = !(S::add(S::mul(dx, dx), S::mul(dy, dy)) > 4.0f);
                 if (d == 1) ok = ok && (c != self);  // sfm.rs:130
                 col[cnt * 32] = static_cast<uint16_t>(c);
                 cnt += ok ? 1u : 0u;
+                po = nxt;
             }
             cur[d] = c;
             more = c < stop[d];
@@ -243,7 +278,7 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
 #pragma unroll 2
         for (uint32_t k = 0; k < cnt; ++k) {
             const uint32_t c = col[k * 32];
-            PairTerm<M>::add(pos, e, tile_pos[c], tile_vel[c], acc);
+            PairTerm<(PEDONI_FAST_PAIR ? M : Math::Strict)>::add(pos, e, tile_pos[c], tile_vel[c], acc);
         }
     } while (more);
 }
@@ -277,8 +312,8 @@ __global__ void __launch_bounds__(kForceThreads, PEDONI_FORCE_MIN_BLOCKS) force_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* tile_pos = reinterpret_cast<float2*>(smem_raw + kWarpSmemBytes * warp);
-    float2* tile_vel = tile_pos + kTileEntries;
-    uint16_t* list = reinterpret_cast<uint16_t*>(tile_vel + kTileEntries);
+    float2* tile_vel = tile_pos + kTileAlloc;
+    uint16_t* list = reinterpret_cast<uint16_t*>(tile_vel + kTileAlloc);
 
     const uint32_t begin = p.d_range[0], end = p.d_range[1];
     const uint32_t block_first = begin + blockIdx.x * kForceThreads;
@@ -346,17 +381,22 @@ __global__ void __launch_bounds__(kForceThreads, PEDONI_FORCE_MIN_BLOCKS) force_
     float2 wall = make_float2(0.f, 0.f);
     if (live) {
         const float2 q = field_coord(pos, p.field);
+        // fast-path guards of field_gradient: through-wall values, and gradients below 0.1 % of the
+        // nominal Sobel magnitude 8 * unit (|grad| = 1 for a distance-like map)
+        const float noise_limit = 1.0e5f * p.field.unit;
+        const float flat_limit2 = (8.0e-3f * p.field.unit) * (8.0e-3f * p.field.unit);
         float gx, gy, unused;
         // dest < n_maps is guaranteed by the rebuild that admitted this agent (sort_key).
         field_gradient<M, false>(p.field.potential_maps + static_cast<size_t>(dest) * p.field.fy * p.field.fx,
-                                 p.field.fy, p.field.fx, q, gx, gy, unused);
+                                 p.field.fy, p.field.fx, q, noise_limit, flat_limit2, gx, gy, unused);
         const float rlen = O::rcp(O::sqrt(O::add(O::mul(gx, gx), O::mul(gy, gy))));
         e = make_float2(O::mul(gx, rlen), O::mul(gy, rlen));
         acc.x = O::add(acc.x, O::div(O::sub(O::mul(e.x, v0), vel.x), 0.5f));
         acc.y = O::add(acc.y, O::div(O::sub(O::mul(e.y, v0), vel.y), 0.5f));
         if (kDistanceMap) {
             float dgx, dgy, distance;
-            field_gradient<M, true>(p.field.distance_map, p.field.fy, p.field.fx, q, dgx, dgy, distance);
+            field_gradient<M, true>(p.field.distance_map, p.field.fy, p.field.fx, q, noise_limit, flat_limit2, dgx, dgy,
+                                    distance);
             const float rl = O::rcp(O::sqrt(O::add(O::mul(dgx, dgx), O::mul(dgy, dgy))));
             const float coef = O::mul(10.0f * 0.2f, O::exp(O::div(-distance, 0.2f)));
             wall = make_float2(O::mul(coef, -O::mul(dgx, rl)), O::mul(coef, -O::mul(dgy, rl)));

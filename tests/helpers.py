@@ -76,3 +76,75 @@ def make_pair(sc, field, options=None, math_mode=0, **kw):
 
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# ---- shipped scenarios (tests/golden/scenarios.npz, made by tests/golden/make_scenarios.py) -----------
+GOLDEN = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+
+
+def scenario_names():
+    z = np.load(GOLDEN / "scenarios.npz")
+    return sorted({k.split("/")[0] for k in z.files if "/" in k})
+
+
+def load_scenario(name):
+    """The reference's scenarios/<name>.toml as a Scenario object."""
+    from pedoni_b200.scenario import PedestrianConfig, PedestrianSpawnConfig
+    z = np.load(GOLDEN / "scenarios.npz")
+    for a in z["__aliases__"]:
+        alias, target = str(a).split("=")
+        if alias == name:
+            name = target
+    sc = scenario_of(z[f"{name}/size"], obstacles=z[f"{name}/obstacles"].tolist(),
+                     waypoints=z[f"{name}/waypoints"].tolist())
+    for origin, dest, kind, value in z[f"{name}/pedestrians"]:
+        spawn = PedestrianSpawnConfig(kind="once", count=int(value)) if kind == 1 else \
+            PedestrianSpawnConfig(kind="periodic", frequency=float(value))
+        sc.pedestrians.append(PedestrianConfig(origin=int(origin), destination=int(dest), spawn=spawn))
+    return sc
+
+
+class OracleAdapter:
+    """The CPU oracle behind the model surface `Simulator` drives (spawn_arrays / rebuild / step / ...)."""
+
+    def __init__(self, options, scenario, field):
+        obs, _ = arrays_of(scenario)
+        self.m = oracle.OracleModel(scenario.field.size, options.neighbor_grid_unit, field.unit, field.distance_map,
+                                    field.potential_maps, obstacles=obs, use_neighbor_grid=options.use_neighbor_grid,
+                                    use_distance_map=options.use_distance_map)
+        self._pending = None
+
+    def spawn_arrays(self, pos, dest, v0):
+        assert self._pending is None
+        self._pending = (pos, dest, v0)
+
+    def rebuild(self):
+        if self._pending is None:
+            self.m.spawn()
+        else:
+            self.m.spawn(*self._pending)
+        self._pending = None
+
+    def step(self):
+        self.m.update()
+
+    def get_pedestrian_count(self):
+        return self.m.count()
+
+    def download(self, vel=True, v0=True):
+        return self.m.get()
+
+    def cell_table(self):
+        return self.m.indices()
+
+
+def simulator_pair(name_or_scenario, seed=1, math_mode=0, options=None, unit=0.25, **cuda_kw):
+    """(cuda Simulator, oracle Simulator) over the same scenario, field arrays and seeded spawn stream."""
+    from pedoni_b200 import SocialForceModelCuda
+    from pedoni_b200.simulator import Simulator
+    sc = load_scenario(name_or_scenario) if isinstance(name_or_scenario, str) else name_or_scenario
+    options = options or SimulatorOptions(field_grid_unit=unit)
+    field = oracle_field(sc, options.field_grid_unit)
+    cu = Simulator(options, sc, field, SocialForceModelCuda(options, sc, field, math_mode=math_mode, **cuda_kw), seed=seed)
+    orc = Simulator(options, sc, field, OracleAdapter(options, sc, field), seed=seed)
+    return cu, orc
