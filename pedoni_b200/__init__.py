@@ -9,4 +9,6 @@ from .model import Pedestrian, SlabGroup, SocialForceModelCuda, comm_unique_id, 
 from .options import Backend, SimulatorOptions  # noqa: F401
 from .scenario import Scenario  # noqa: F401
 from .field import Field  # noqa: F401
+from .simulator import Simulator, SpawnStream, StepMetrics  # noqa: F401
+from . import observables  # noqa: F401
 from ._capi import (PEDONI_MATH_FAST, PEDONI_MATH_STRICT, PedoniError)  # noqa: F401
