@@ -257,32 +257,42 @@ def run_ours(args):
         s_pos, s_dest, s_v0 = pin((nb, 2), torch.float32), pin((nb,), torch.int32).view(np.uint32), \
             pin((nb,), torch.float32)
         extra = SyntheticCrowd(n=args.agents, density=args.density, seed=crowd.seed ^ 0xE2E)
-        d2h = 0
+        h_pos2, h_dest2 = pin((cap, 2), torch.float32), pin((cap,), torch.int32).view(np.uint32)
+        bufs = [(h_pos, h_dest), (h_pos2, h_dest2)]
+        state = {"inflight": False, "n": 0, "bytes": 0}
+
+        def collect():
+            """Finish the pipelined list_pedestrians of the previous tick: its payload is on the host now."""
+            if state["inflight"]:
+                pos, dest = model.download_end()
+                state["n"] += pos.shape[0]
+                state["bytes"] = pos.nbytes + dest.nbytes
+                state["inflight"] = False
 
         def e2e_tick(k):
-            nonlocal d2h
             p, d, _, v = extra.agents(k * nb, (k + 1) * nb)  # synthetic inflow, uniform over the domain
             s_pos[:], s_dest[:], s_v0[:] = p, d, v
             model.spawn_arrays(s_pos, s_dest, s_v0)   # H2D (spawn_pedestrians, first half)
             model.rebuild()                           # spawn_pedestrians, second half
             model.step()                              # update_states
-            pos, dest, _, _ = model.download(vel=False, v0=False, out=(h_pos, h_dest, None, None))  # list_pedestrians
-            d2h = pos.nbytes + dest.nbytes
-            return pos.shape[0]
+            collect()                                 # tick k-1's pedestrians arrived while tick k was computed
+            model.download_begin(*bufs[k % 2])        # list_pedestrians of tick k: device snapshot + async D2H
+            state["inflight"] = True
 
         for k in range(max(args.warmup, 1)):
             e2e_tick(k)
+        collect()
+        state["n"] = 0
         barrier()
         t0 = time.perf_counter()
-        model.timer_begin()
-        n_e2e = 0
         for k in range(args.steps):
-            n_e2e += e2e_tick(args.warmup + 1 + k)
-        ms_e2e = model.timer_end()
-        torch.cuda.synchronize()
+            e2e_tick(args.warmup + 1 + k)
+        collect()                                     # every timed tick's result has been read on the host
+        model.synchronize()
         wall_e2e = (time.perf_counter() - t0) * 1e3
         barrier()
-        te = torch.tensor([max(ms_e2e, wall_e2e), float(n_e2e), float(d2h)], dtype=torch.float64, device="cuda")
+        n_e2e, d2h = state["n"], state["bytes"]
+        te = torch.tensor([wall_e2e, float(n_e2e), float(d2h)], dtype=torch.float64, device="cuda")
         if world > 1:
             tm = te.clone()
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -294,7 +304,10 @@ def run_ours(args):
         e2e = {"value": e_updates / (e_ms * 1e-3), "unit": "updates/s",
                "h2d_bytes_per_step": nb * 16 * world, "d2h_bytes_per_step": int(e_d2h),
                "ms_per_step": e_ms / args.steps,
-               "api": "pedoni_spawn + pedoni_rebuild + pedoni_step + pedoni_download(pos, destination)"}
+               "timer": "host wall clock around the K ticks (device events cannot see the D2H stream)",
+               "api": "pedoni_spawn + pedoni_rebuild + pedoni_step + pedoni_download_begin/_end(pos, destination): "
+                      "list_pedestrians of tick k travels while tick k+1 is computed; all K payloads are on the "
+                      "host before the clock stops"}
 
     clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
     sampler.stop()

@@ -139,6 +139,18 @@ int32_t pedoni_count(PedoniModel* model);
 int pedoni_download(PedoniModel* model, float* pos_xy, uint32_t* destination, float* vel_xy,
                     float* desired_speed, uint32_t cap, uint32_t* n_out);
 
+/*
+ * list_pedestrians without stalling the model (the reference copies every pedestrian to the host every
+ * tick, main.rs:95). pedoni_download_begin snapshots (position, destination) of the owned pedestrians on
+ * the device behind the work already enqueued and starts copying the snapshot to the caller's buffers
+ * on a separate stream; it returns at once, and spawn / rebuild / step may be called meanwhile.
+ * pedoni_download_end blocks until the copy has landed and reports how many pedestrians were written.
+ * The buffers must stay valid (pinned memory makes the copy truly asynchronous) until _end returns; one
+ * pipelined download may be in flight per handle. Needs a rebuilt state (no pending pedoni_spawn).
+ */
+int pedoni_download_begin(PedoniModel* model, float* pos_xy, uint32_t* destination, uint32_t cap);
+int pedoni_download_end(PedoniModel* model, uint32_t* n_out);
+
 /* Replace the whole agent state (parity tests, checkpoint restore). Unsorted: call pedoni_rebuild. */
 int pedoni_upload_state(PedoniModel* model, uint32_t n, const float* pos_xy, const uint32_t* destination,
                         const float* vel_xy, const float* desired_speed);

@@ -102,6 +102,17 @@ struct PedoniModel {
     bool table_valid = false;  // d_cell_start indexes buf[cur]
     bool ever_rebuilt = false;
 
+    // pipelined list_pedestrians (pedoni_download_begin / _end)
+    cudaStream_t dl_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_dl_done = nullptr;
+    float2* d_snap_pos = nullptr;
+    uint32_t* d_snap_dest = nullptr;
+    uint32_t* d_snap_range = nullptr;  // owned [begin, end) copied on the main stream with the snapshot
+    uint32_t snap_cap = 0;
+    uint32_t* h_snap_range = nullptr;  // pinned: owned [begin, end) at snapshot time
+    bool dl_inflight = false;
+    uint32_t dl_cap = 0;
+
     bool profiling = false;
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -659,6 +670,16 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_recv_above})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
+    if (m->dl_stream) {
+        cudaStreamSynchronize(m->dl_stream);
+        cudaStreamDestroy(m->dl_stream);
+    }
+    for (cudaEvent_t e : {m->ev_snap, m->ev_dl_done})
+        if (e) cudaEventDestroy(e);
+    cudaFree(m->d_snap_pos);
+    cudaFree(m->d_snap_dest);
+    cudaFree(m->d_snap_range);
+    if (m->h_snap_range) cudaFreeHost(m->h_snap_range);
     if (m->edge_stream) cudaStreamDestroy(m->edge_stream);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -953,6 +974,72 @@ int pedoni_download(PedoniModel* m, float* pos_xy, uint32_t* dest, float* vel_xy
     CUDA_TRY(m, pull(v0, a.v0, m->app.v0, sizeof(float)));
     CUDA_TRY(m, cudaStreamSynchronize(m->stream));
     if (cap < n) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", cap, n);
+    return PEDONI_OK;
+}
+
+// Pipelined list_pedestrians: snapshot the owned (pos, destination) columns on the device (one D2D pass
+// behind the work already enqueued), then copy the snapshot to the caller's buffers on a separate
+// stream. The model may keep stepping meanwhile; pedoni_download_end waits for the copy.
+int pedoni_download_begin(PedoniModel* m, float* pos_xy, uint32_t* dest, uint32_t cap) {
+    if (!m || !pos_xy || !dest) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (m->dl_inflight) return fail(m, PEDONI_ERR_STATE, "a pipelined download is already in flight");
+    if (m->app_n > 0) return fail(m, PEDONI_ERR_STATE, "pedoni_download_begin with un-rebuilt spawns");
+    if (!m->dl_stream) {
+        CUDA_TRY(m, cudaStreamCreateWithFlags(&m->dl_stream, cudaStreamNonBlocking));
+        CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_dl_done, cudaEventDisableTiming));
+        CUDA_TRY(m, cudaHostAlloc(&m->h_snap_range, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        CUDA_TRY(m, cudaMalloc(&m->d_snap_range, 2 * sizeof(uint32_t)));
+    }
+    const uint32_t upper = m->owned_upper;  // host bound of the owned population; the exact count follows
+    if (upper > m->snap_cap) {
+        CUDA_TRY(m, cudaStreamSynchronize(m->dl_stream));
+        cudaFree(m->d_snap_pos);
+        cudaFree(m->d_snap_dest);
+        m->d_snap_pos = nullptr;
+        m->d_snap_dest = nullptr;
+        const uint32_t ncap = std::max<uint32_t>(upper + upper / 8, 1024);
+        CUDA_TRY(m, cudaMalloc(&m->d_snap_pos, sizeof(float2) * (size_t)ncap));
+        CUDA_TRY(m, cudaMalloc(&m->d_snap_dest, sizeof(uint32_t) * (size_t)ncap));
+        m->snap_cap = ncap;
+    }
+    const AgentArrays& a = m->buf[m->cur];
+    const uint32_t take = std::min(upper, cap);
+    // the previous copy out of the snapshot buffers finished before pedoni_download_end returned
+    if (upper) {
+        CUDA_TRY(m, cudaMemcpyAsync(m->d_snap_pos, a.pos + m->array_offset, sizeof(float2) * (size_t)upper,
+                                    cudaMemcpyDeviceToDevice, m->stream));
+        CUDA_TRY(m, cudaMemcpyAsync(m->d_snap_dest, a.dest + m->array_offset, sizeof(uint32_t) * (size_t)upper,
+                                    cudaMemcpyDeviceToDevice, m->stream));
+    }
+    CUDA_TRY(m, cudaMemcpyAsync(m->d_snap_range, m->range(kRangeOwned), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                m->stream));  // the next rebuild rewrites d_ranges: freeze the count with the data
+    CUDA_TRY(m, cudaEventRecord(m->ev_snap, m->stream));
+    CUDA_TRY(m, cudaStreamWaitEvent(m->dl_stream, m->ev_snap, 0));
+    CUDA_TRY(m, cudaMemcpyAsync(m->h_snap_range, m->d_snap_range, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                m->dl_stream));
+    if (take) {
+        CUDA_TRY(m, cudaMemcpyAsync(pos_xy, m->d_snap_pos, sizeof(float2) * (size_t)take, cudaMemcpyDeviceToHost,
+                                    m->dl_stream));
+        CUDA_TRY(m, cudaMemcpyAsync(dest, m->d_snap_dest, sizeof(uint32_t) * (size_t)take, cudaMemcpyDeviceToHost,
+                                    m->dl_stream));
+    }
+    CUDA_TRY(m, cudaEventRecord(m->ev_dl_done, m->dl_stream));
+    m->dl_inflight = true;
+    m->dl_cap = cap;
+    return PEDONI_OK;
+}
+
+int pedoni_download_end(PedoniModel* m, uint32_t* n_out) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (!m->dl_inflight) return fail(m, PEDONI_ERR_STATE, "no pipelined download in flight");
+    CUDA_TRY(m, cudaEventSynchronize(m->ev_dl_done));
+    m->dl_inflight = false;
+    const uint32_t n = m->h_snap_range[1] - m->h_snap_range[0];
+    if (n_out) *n_out = n;
+    if (n > m->dl_cap) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", m->dl_cap, n);
     return PEDONI_OK;
 }
 

@@ -144,6 +144,17 @@ class SocialForceModelCuda:
         k = n_out.value
         return pos[:k], dest[:k], (velo[:k] if velo is not None else None), (v0o[:k] if v0o is not None else None)
 
+    def download_begin(self, pos: np.ndarray, dest: np.ndarray) -> None:
+        """Pipelined `list_pedestrians`: snapshot on the device, copy to (pinned) `pos`/`dest` in the background."""
+        self._dl = (pos, dest)  # keep the buffers alive until download_end
+        _capi.check(self._lib.pedoni_download_begin(self._h, _fp(pos), _up(dest), dest.shape[0]), self._h)
+
+    def download_end(self):
+        n = C.c_uint32()
+        _capi.check(self._lib.pedoni_download_end(self._h, C.byref(n)), self._h)
+        pos, dest = self._dl
+        return pos[: n.value], dest[: n.value]
+
     def grid_shape(self):
         ny, nx = C.c_int32(), C.c_int32()
         _capi.check(self._lib.pedoni_grid_shape(self._h, C.byref(ny), C.byref(nx)), self._h)

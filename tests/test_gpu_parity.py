@@ -155,3 +155,29 @@ def test_empty_model_and_errors(corridor):
         cu.step()
     with pytest.raises(PedoniError):  # O(N^2) path is not built
         helpers.make_pair(sc, field, options=SimulatorOptions(use_neighbor_grid=False))
+
+
+def test_pipelined_download_equals_blocking_download(corridor):
+    """pedoni_download_begin/_end: the snapshot is of the moment of the call, whatever is enqueued after it."""
+    import torch
+    sc, field = corridor
+    cu, _ = helpers.make_pair(sc, field)
+    pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=9, margin=4.0)
+    cu.upload_state(pos, dest, vel, v0)
+    cu.rebuild()
+    h_pos = torch.empty((4000, 2), dtype=torch.float32).pin_memory().numpy()
+    h_dest = torch.empty(4000, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    for _ in range(5):
+        cu.step()
+        want_pos, want_dest = cu.download(vel=False, v0=False)[:2]
+        cu.download_begin(h_pos, h_dest)
+        cu.rebuild()          # the model moves on while the copy is in flight
+        cu.step()
+        cu.rebuild()
+        got_pos, got_dest = cu.download_end()
+        np.testing.assert_array_equal(bits(got_pos), bits(want_pos))
+        np.testing.assert_array_equal(got_dest, want_dest)
+    from pedoni_b200 import PedoniError
+    with pytest.raises(PedoniError):
+        cu.download_end()     # nothing in flight
+    cu.close()
