@@ -352,6 +352,10 @@ def run_ours(args):
 
 
 if __name__ == "__main__":
+    # Rank 0 prints exactly ONE line on stdout: libraries (NCCL prints its version banner) get stderr.
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w")
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -92,7 +92,7 @@ typedef struct PedoniConfig {
     void* stream;                /* optional cudaStream_t to enqueue on (NULL: the handle owns one) */
 
     /* Slab handles: capacity, in pedestrians, of one two-row ghost strip (= of one halo message).
-     * 0 = auto (4x the two-row population of a uniformly filled slab of `capacity` agents, >= 4096).
+     * 0 = auto (3x the two-row population of a uniformly filled slab of `capacity` agents, >= 4096).
      * All slabs of one decomposition must use the same value. */
     uint32_t halo_capacity;
 } PedoniConfig;

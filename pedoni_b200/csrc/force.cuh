@@ -77,6 +77,8 @@ struct ForceParams {
     GridView grid;
     FieldView field;
     uint32_t* keys_out;          // next rebuild's keys, indexed like the arrays
+    uint32_t* ticket_out;        // next rebuild's in-cell slots (the histogram is fused here)
+    uint32_t* cell_count;        // per-cell population of the NEXT rebuild (zeroed by the previous one)
     uint32_t* error_flag;
     unsigned long long* updates_total;  // += owned agents of this launch (thread 0 of block 0)
     const float* obstacle_edges;  // segment-wall variant only
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(kForceThreads, PEDONI_FORCE_MIN_BLOCKS) force_
     p.out.vel[id] = vn;
     p.out.v0[id] = v0;
     p.out.dest[id] = dest;
-    p.keys_out[id] = sort_key(p.grid, p.field, pn, dest, p.error_flag);
+    count_key(sort_key(p.grid, p.field, pn, dest, p.error_flag), p.cell_count, p.keys_out + id, p.ticket_out + id);
     // Slab handles exchange two ghost rows per tick, which covers every move of less than one grid row
     // (1.4 m per 0.1 s); anything faster would silently vanish at a slab boundary, so flag it.
     if (p.grid.slab) {

@@ -4,10 +4,10 @@
 // Replaces NeighborGrid::update (neighbor_grid.rs:22-36) and the serial walk/gather of
 // SocialForceModel::spawn_pedestrians (sfm.rs:58-77):
 //
-//   key        cell key per agent (fused into the force kernel's epilogue for agents that were just
-//              integrated; this kernel only handles freshly spawned / uploaded agents)
-//   histogram  per-cell population (atomicAdd on the cell counter; the returned ticket is a unique
-//              but order-arbitrary slot inside the cell)
+//   key        cell key per agent + per-cell population (atomicAdd on the cell counter; the returned
+//              ticket is a unique but order-arbitrary slot inside the cell). Fused into the force kernel's
+//              epilogue for agents that were just integrated; key_kernel only handles freshly spawned /
+//              uploaded agents. The counters are zeroed at the end of every rebuild.
 //   scan       exclusive prefix over cells, built from block-wide scans -> `neighbor_grid_indices`
 //              (sfm.rs:61-75), length cells + 1
 //   scatter    perm[start[cell] + ticket] = logical input index
@@ -57,6 +57,7 @@ constexpr int kMaxSegments = 2;
 struct Segment {
     AgentArrays a;
     uint32_t* keys;           // sort keys, indexed like the arrays
+    uint32_t* ticket;         // slot inside the cell (kKeyDrop: not kept), indexed like the arrays
     const uint32_t* d_range;  // device: [begin, end) of live entries inside the arrays; nullptr = [0, upper)
     uint32_t upper;           // host-known upper bound of (end - begin)
 };
@@ -73,6 +74,7 @@ struct SortInput {
 struct Located {
     AgentArrays a;
     uint32_t* keys;
+    uint32_t* ticket;
     uint32_t idx;
     bool live;
 };
@@ -86,6 +88,7 @@ __device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
     r.a.v0 = second ? in.seg[1].a.v0 : in.seg[0].a.v0;
     r.a.dest = second ? in.seg[1].a.dest : in.seg[0].a.dest;
     r.keys = second ? in.seg[1].keys : in.seg[0].keys;
+    r.ticket = second ? in.seg[1].ticket : in.seg[0].ticket;
     const uint32_t* d_range = second ? in.seg[1].d_range : in.seg[0].d_range;
     // d_range == nullptr: the population is host-known, [0, upper) (appended spawns).
     uint32_t begin = 0, end = second ? in.seg[1].upper : in.seg[0].upper;
@@ -98,31 +101,25 @@ __device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
     return r;
 }
 
+// Key + population count of one agent: shared by key_kernel and the force kernel's epilogue.
+__device__ __forceinline__ void count_key(uint32_t key, uint32_t* __restrict__ cell_count, uint32_t* key_slot,
+                                          uint32_t* ticket_slot) {
+    *key_slot = key;
+    *ticket_slot = key < kKeyFirstSpecial ? atomicAdd(cell_count + key, 1u) : kKeyDrop;
+}
+
 // ---- key: only for logical indices in [t_begin, t_end) whose keys are not fresh -------------------
 __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin, uint32_t t_end, GridView g,
-                                                  FieldView f, uint32_t* __restrict__ error_flag) {
+                                                  FieldView f, uint32_t* __restrict__ cell_count,
+                                                  uint32_t* __restrict__ error_flag) {
     uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
     const Located l = locate(in, t);
     if (!l.live) return;
     // Spawn lists are replicated to every slab and ghost rows are copies: sort_key keeps an agent only
     // on the handle that owns its row.
-    l.keys[l.idx] = sort_key(g, f, l.a.pos[l.idx], l.a.dest[l.idx], error_flag);
-}
-
-// ---- histogram -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) histogram_kernel(SortInput in, uint32_t total_upper,
-                                                        uint32_t* __restrict__ cell_count,
-                                                        uint32_t* __restrict__ ticket) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_upper) return;
-    uint32_t tk = kKeyDrop;  // ticket[t] == kKeyDrop <=> logical index t is not kept
-    const Located l = locate(in, t);
-    if (l.live) {
-        uint32_t key = l.keys[l.idx];
-        if (key < kKeyFirstSpecial) tk = atomicAdd(cell_count + key, 1u);
-    }
-    ticket[t] = tk;
+    count_key(sort_key(g, f, l.a.pos[l.idx], l.a.dest[l.idx], error_flag), cell_count, l.keys + l.idx,
+              l.ticket + l.idx);
 }
 
 // ---- scan: exclusive prefix over n_cells counters, three launches built from block-wide scans -----
@@ -217,27 +214,27 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 
 // ---- scatter: perm[start[cell] + ticket] = t -----------------------------------------------------
 __global__ void __launch_bounds__(256) scatter_kernel(SortInput in, uint32_t total_upper,
-                                                      const uint32_t* __restrict__ ticket,
                                                       const uint32_t* __restrict__ cell_start,
                                                       uint32_t* __restrict__ perm) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_upper) return;
-    const uint32_t tk = ticket[t];
-    if (tk == kKeyDrop) return;
     const Located l = locate(in, t);
+    if (!l.live) return;
+    const uint32_t tk = l.ticket[l.idx];
+    if (tk == kKeyDrop) return;
     perm[__ldg(cell_start + l.keys[l.idx]) + tk] = t;
 }
 
 // ---- gather: stable rank inside the cell, then move the 24-byte state ----------------------------
 __global__ void __launch_bounds__(256) gather_kernel(SortInput in, uint32_t total_upper,
-                                                     const uint32_t* __restrict__ ticket,
                                                      const uint32_t* __restrict__ cell_start,
                                                      const uint32_t* __restrict__ perm, AgentArrays out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_upper) return;
-    if (ticket[t] == kKeyDrop) return;
     const Located l = locate(in, t);
+    if (!l.live) return;
     const uint32_t idx = l.idx;
+    if (l.ticket[idx] == kKeyDrop) return;
     const uint32_t key = l.keys[idx];
     const uint32_t begin = __ldg(cell_start + key), end = __ldg(cell_start + key + 1);
     uint32_t rank = 0;

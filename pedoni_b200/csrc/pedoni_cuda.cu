@@ -72,15 +72,16 @@ struct PedoniModel {
     cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_peer = nullptr;
 
     AgentArrays buf[2]{};
-    uint32_t* d_keys[2] = {nullptr, nullptr};  // sort keys, indexed like buf[k]
+    uint32_t* d_keys[2] = {nullptr, nullptr};    // sort keys, indexed like buf[k]
+    uint32_t* d_tickets[2] = {nullptr, nullptr};  // in-cell slots, indexed like buf[k]
     uint32_t cap = 0;          // elements per array
     int cur = 0;
     uint32_t owned_upper = 0;  // host upper bound of owned agents in buf[cur]
     AgentArrays app{};         // appended spawns, not yet rebuilt
     uint32_t* d_keys_app = nullptr;
+    uint32_t* d_tickets_app = nullptr;
     uint32_t app_cap = 0, app_n = 0;
 
-    uint32_t* d_ticket = nullptr;
     uint32_t* d_perm = nullptr;
     uint32_t aux_cap = 0;
     uint32_t* d_cell_count = nullptr;
@@ -200,19 +201,24 @@ int ensure_capacity(PedoniModel* m, uint32_t need_arrays, uint32_t need_aux) {
         ncap = std::max<uint32_t>(ncap, 1024);
         for (int b = 0; b < 2; ++b) {
             AgentArrays fresh{};
-            uint32_t* fresh_keys = nullptr;
+            uint32_t *fresh_keys = nullptr, *fresh_tickets = nullptr;
             CUDA_TRY(m, alloc_agents(fresh, ncap));
             CUDA_TRY(m, cudaMalloc(&fresh_keys, sizeof(uint32_t) * (size_t)ncap));
+            CUDA_TRY(m, cudaMalloc(&fresh_tickets, sizeof(uint32_t) * (size_t)ncap));
             if (b == m->cur && m->cap > 0) {
                 CUDA_TRY(m, copy_agents(fresh, m->buf[b], m->cap, m->stream));
                 CUDA_TRY(m, cudaMemcpyAsync(fresh_keys, m->d_keys[b], sizeof(uint32_t) * (size_t)m->cap,
+                                            cudaMemcpyDeviceToDevice, m->stream));
+                CUDA_TRY(m, cudaMemcpyAsync(fresh_tickets, m->d_tickets[b], sizeof(uint32_t) * (size_t)m->cap,
                                             cudaMemcpyDeviceToDevice, m->stream));
             }
             CUDA_TRY(m, cudaStreamSynchronize(m->stream));
             free_agents(m->buf[b]);
             cudaFree(m->d_keys[b]);
+            cudaFree(m->d_tickets[b]);
             m->buf[b] = fresh;
             m->d_keys[b] = fresh_keys;
+            m->d_tickets[b] = fresh_tickets;
         }
         m->cap = ncap;
     }
@@ -221,10 +227,8 @@ int ensure_capacity(PedoniModel* m, uint32_t need_arrays, uint32_t need_aux) {
         if (rc != PEDONI_OK) return rc;
         uint32_t ncap = std::max<uint32_t>(need_aux, m->aux_cap + m->aux_cap / 2);
         ncap = std::max<uint32_t>(ncap, 1024);
-        cudaFree(m->d_ticket);
         cudaFree(m->d_perm);
-        m->d_ticket = m->d_perm = nullptr;
-        CUDA_TRY(m, cudaMalloc(&m->d_ticket, sizeof(uint32_t) * (size_t)ncap));
+        m->d_perm = nullptr;
         CUDA_TRY(m, cudaMalloc(&m->d_perm, sizeof(uint32_t) * (size_t)ncap));
         m->aux_cap = ncap;
     }
@@ -236,15 +240,18 @@ int ensure_app_capacity(PedoniModel* m, uint32_t need) {
     uint32_t ncap = std::max<uint32_t>(need, m->app_cap * 2);
     ncap = std::max<uint32_t>(ncap, 1024);
     AgentArrays fresh{};
-    uint32_t* fresh_keys = nullptr;
+    uint32_t *fresh_keys = nullptr, *fresh_tickets = nullptr;
     CUDA_TRY(m, alloc_agents(fresh, ncap));
     CUDA_TRY(m, cudaMalloc(&fresh_keys, sizeof(uint32_t) * (size_t)ncap));
+    CUDA_TRY(m, cudaMalloc(&fresh_tickets, sizeof(uint32_t) * (size_t)ncap));
     CUDA_TRY(m, copy_agents(fresh, m->app, m->app_n, m->stream));
     CUDA_TRY(m, cudaStreamSynchronize(m->stream));
     free_agents(m->app);
     cudaFree(m->d_keys_app);
+    cudaFree(m->d_tickets_app);
     m->app = fresh;
     m->d_keys_app = fresh_keys;
+    m->d_tickets_app = fresh_tickets;
     m->app_cap = ncap;
     return PEDONI_OK;
 }
@@ -344,8 +351,9 @@ void build_edges(const float* obstacles, int n, std::vector<float>& out) {
 SortInput make_sort_input(PedoniModel* m) {
     SortInput in{};
     in.nseg = 2;
-    in.seg[0] = Segment{m->buf[m->cur], m->d_keys[m->cur], m->range(kRangeCompute), m->compute_upper()};
-    in.seg[1] = Segment{m->app, m->d_keys_app, nullptr, m->app_n};
+    in.seg[0] = Segment{m->buf[m->cur], m->d_keys[m->cur], m->d_tickets[m->cur], m->range(kRangeCompute),
+                        m->compute_upper()};
+    in.seg[1] = Segment{m->app, m->d_keys_app, m->d_tickets_app, nullptr, m->app_n};
     in.prefix[0] = 0;
     in.prefix[1] = m->compute_upper();
     in.prefix[2] = m->compute_upper() + m->app_n;
@@ -371,6 +379,8 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     p.grid = m->grid;
     p.field = m->field;
     p.keys_out = m->d_keys[m->cur ^ 1];
+    p.ticket_out = m->d_tickets[m->cur ^ 1];
+    p.cell_count = m->d_cell_count;
     p.error_flag = m->d_error;
     p.updates_total = m->d_updates;
     p.obstacle_edges = m->d_edges;
@@ -574,15 +584,20 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     if (m->slab_count > 1) {
         if (c->halo_capacity) {
             m->halo_cap = c->halo_capacity;
-        } else {  // 4x the two-row population of a uniformly filled slab
+        } else {  // 3x the two-row population of a uniformly filled slab
             // (same on every rank: the message size must agree, so use the common floor of rows per slab)
             const uint64_t per_row = capacity / static_cast<uint32_t>(m->grid.ny / m->slab_count) + 1;
-            m->halo_cap = static_cast<uint32_t>(std::max<uint64_t>(4096, 8 * per_row));
+            m->halo_cap = static_cast<uint32_t>(std::max<uint64_t>(4096, 6 * per_row));
         }
         m->halo_cap = (m->halo_cap + 255u) & ~255u;
         m->array_offset = m->has_below ? m->halo_cap : 0;
         m->msg_bytes = halo_message_words(m->grid.nx, m->halo_cap) * sizeof(uint32_t);
-        CREATE_TRY(cudaStreamCreateWithFlags(&m->edge_stream, cudaStreamNonBlocking));
+        // Highest priority: the exchange, unpack and edge kernels are tiny but sit behind tens of thousands
+        // of queued CTAs of the interior force kernel; without priority they are dispatched only when that
+        // kernel drains (measured at 8 GPUs: exchange 167 us ~ the whole interior kernel).
+        int prio_least = 0, prio_greatest = 0;
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CREATE_TRY(cudaStreamCreateWithPriority(&m->edge_stream, cudaStreamNonBlocking, prio_greatest));
         for (uint32_t** b : {&m->d_send_dn, &m->d_send_up, &m->d_recv_below, &m->d_recv_above}) {
             CREATE_TRY(cudaMalloc(b, m->msg_bytes));
             CREATE_TRY(cudaMemsetAsync(*b, 0, m->msg_bytes, m->stream));
@@ -631,6 +646,7 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     CREATE_TRY(cudaMalloc(&m->d_updates, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(m->d_updates, 0, sizeof(unsigned long long), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_cell_start, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
+    CREATE_TRY(cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
     CREATE_TRY(cudaHostAlloc(&m->h_pub, sizeof(unsigned long long) * 2, cudaHostAllocMapped));
     m->h_pub[0] = m->h_pub[1] = 0;
@@ -663,7 +679,8 @@ void pedoni_destroy(PedoniModel* m) {
     free_agents(m->buf[0]);
     free_agents(m->buf[1]);
     free_agents(m->app);
-    for (void* p : {(void*)m->d_keys[0], (void*)m->d_keys[1], (void*)m->d_keys_app, (void*)m->d_ticket, (void*)m->d_perm,
+    for (void* p : {(void*)m->d_keys[0], (void*)m->d_keys[1], (void*)m->d_keys_app, (void*)m->d_tickets[0], (void*)m->d_tickets[1], (void*)m->d_tickets_app,
+                    (void*)m->d_perm,
                     (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_sums, (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_distance, (void*)m->d_potential,
                     (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_recv_below,
@@ -737,6 +754,8 @@ int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const u
         m->halo_inflight = false;
     }
     advance_tick(m, 0);
+    // a preceding pedoni_step has already counted the (now discarded) residents into the next histogram
+    CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, m->stream));
     reset_layout_kernel<<<1, 1, 0, m->stream>>>(m->d_ranges, m->array_offset, m->h_pub_dev, m->tick);
     m->launches += 1;
     m->owned_upper = 0;
@@ -759,18 +778,13 @@ static int rebuild_impl(PedoniModel* m) {
     SortInput in = make_sort_input(m);
 
     if (total > 0) {
+        // Keys + per-cell counts of the resident agents were produced by the force kernel's epilogue; only
+        // appended spawns (or everything, when no step preceded this rebuild) are keyed here.
         const uint32_t t_begin = m->keys_fresh ? resident : 0u;
         if (t_begin < total) {
             ScopedTimer t(m, kKey, s);
-            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field, m->d_error);
-            m->launches += 1;
-        }
-    }
-    {
-        ScopedTimer t(m, kHistogram, s);
-        CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
-        if (total > 0) {
-            histogram_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_count, m->d_ticket);
+            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field,
+                                                                   m->d_cell_count, m->d_error);
             m->launches += 1;
         }
     }
@@ -780,18 +794,19 @@ static int rebuild_impl(PedoniModel* m) {
         scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(m->d_tile_sums, m->n_tiles);
         scan_apply_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums,
                                                               m->array_offset, m->d_cell_start);
+        // zero the counters for the next tick's fused histogram (force epilogue / key_kernel)
+        CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
         m->launches += 3;
     }
     if (total > 0) {
         {
             ScopedTimer t(m, kScatter, s);
-            scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_ticket, m->d_cell_start, m->d_perm);
+            scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm);
             m->launches += 1;
         }
         {
             ScopedTimer t(m, kGather, s);
-            gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_ticket, m->d_cell_start, m->d_perm,
-                                                            m->buf[m->cur ^ 1]);
+            gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm, m->buf[m->cur ^ 1]);
             m->launches += 1;
         }
     }
