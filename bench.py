@@ -31,6 +31,10 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 ALGO_BYTES_PER_UPDATE = 48  # read 24 B state + write 24 B state
+# DRAM bytes the force kernel actually moves per update: dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` launch at this workload (profiles/r01f_force_10M_full.md: 2.191 GB + 0.340 GB for
+# 9 997 570 pedestrians). The excess over 48 B is the field maps: two 4x4 texel footprints per pedestrian.
+NCU_TRAFFIC_BYTES_PER_UPDATE = (2.191440e9 + 339.557632e6) / 9997570
 RELAX_STEPS = 50            # untimed: lets the zero-velocity seed crowd reach walking state
 E2E_SPAWN_PER_STEP = 1024   # host->device spawn batch per e2e step
 
@@ -269,8 +273,13 @@ def run_ours(args):
                 state["bytes"] = pos.nbytes + dest.nbytes
                 state["inflight"] = False
 
+        # the synthetic inflow (uniform over the domain) is drawn before the clock starts: generating random
+        # numbers in numpy is not part of the path, copying them into the pinned staging buffers is
+        n_ticks = max(args.warmup, 1) + args.steps + 2
+        inflow = [extra.agents(k * nb, (k + 1) * nb) for k in range(n_ticks)]
+
         def e2e_tick(k):
-            p, d, _, v = extra.agents(k * nb, (k + 1) * nb)  # synthetic inflow, uniform over the domain
+            p, d, _, v = inflow[k]
             s_pos[:], s_dest[:], s_v0[:] = p, d, v
             model.spawn_arrays(s_pos, s_dest, s_v0)   # H2D (spawn_pedestrians, first half)
             model.rebuild()                           # spawn_pedestrians, second half
@@ -335,11 +344,17 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "force_integrate_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (NCU_TRAFFIC_BYTES_PER_UPDATE * agents_per_launch
+                                     if args.math == "fast" and args.density == 1.0 else None),
+                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01f_force_10M_full.md, "
+                                         "scaled by pedestrians per launch)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                          "kernel_ms_per_launch": force_ms, "agents_per_launch": agents_per_launch,
-                         "note": "at 1 ped/m^2 the kernel is FP32/SFU-issue bound, not HBM bound "
-                                 "(~18 candidate pairs per update); see DESIGN.md"},
+                         "note": "at 1 ped/m^2 the kernel is instruction-issue bound (75 % of issue slots, ncu), "
+                                 "not HBM bound: ~18 candidate pairs per update; the field maps add ~205 B of "
+                                 "compulsory reads per update to the 48 algorithmic bytes; see DESIGN.md"},
             "kernel_ms_per_step": step_kernel_ms,
             "clocks": clocks,
         }
