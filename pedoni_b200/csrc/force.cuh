@@ -146,26 +146,29 @@ struct PairTerm<Math::Fast> {
         return r;
     }
     static __device__ __forceinline__ void add(float2 pos, float2 e, float2 po, float2 vo, float2& acc) {
-        const float dx = pos.x - po.x, dy = pos.y - po.y;
-        const float d2 = fmaf(dy, dy, dx * dx);
+        // Vec2 operations as packed fp32x2 (FFMA2): one issue slot for both components.
+        const f32x2 d2v = sub2(pack2(pos), pack2(po));
+        const float2 d = unpack2(d2v);
+        const float d2 = fmaf(d.y, d.y, d.x * d.x);
         const float rinv = rsqrt(d2);
-        const float wx = 0.1f * vo.x, wy = 0.1f * vo.y;
-        const float t1x = dx - wx, t1y = dy - wy;
-        const float t1sq = fmaf(t1y, t1y, t1x * t1x);
+        const f32x2 t1v = fma2(pack2(vo), pack2(-0.1f, -0.1f), d2v);  // d - 0.1 v_i
+        const float2 t1 = unpack2(t1v);
+        const float vv = fmaf(vo.y, vo.y, vo.x * vo.x);
+        const float t1sq = fmaf(t1.y, t1.y, t1.x * t1.x);
         const float rt1 = rsqrt(t1sq);
         const float t2 = fmaf(d2, rinv, t1sq * rt1);  // |d| + |t1|
-        const float q = fmaf(t2, t2, -fmaf(wy, wy, wx * wx));
+        const float q = fmaf(vv, -0.01f, t2 * t2);    // t2^2 - |0.1 v_i|^2
         const float rq = rsqrt(q);
         constexpr float kC = -1.4426950408889634f / 0.6f;  // exp(-b/0.3), b = sqrt(q)/2, as exp2
         constexpr float kLog2K = 1.8073549220576042f;      // log2(2.1 / 0.3 / 2)
         float s = ex2(fmaf(q * rq, kC, kLog2K)) * (t2 * rq);
-        const float nx = fmaf(t1x, rt1, dx * rinv), ny = fmaf(t1y, rt1, dy * rinv);
-        const float en = fmaf(e.y, ny, e.x * nx);
-        const float n2 = fmaf(ny, ny, nx * nx);
+        const f32x2 nv = fma2(t1v, pack2(rt1, rt1), mul2(d2v, pack2(rinv, rinv)));  // d/|d| + t1/|t1|
+        const float2 n = unpack2(nv);
+        const float en = fmaf(e.y, n.y, e.x * n.x);
+        const float n2 = fmaf(n.y, n.y, n.x * n.x);
         constexpr float kCos2 = kCosPhi * kCosPhi;
         if (en > 0.0f && en * en > kCos2 * n2) s *= 0.5f;
-        acc.x = fmaf(s, nx, acc.x);
-        acc.y = fmaf(s, ny, acc.y);
+        acc = unpack2(fma2(pack2(s, s), nv, pack2(acc)));
     }
 };
 
@@ -251,6 +254,7 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
                                                   uint32_t (&cur)[3], const uint32_t (&stop)[3], uint32_t self,
                                                   float2& acc) {
     uint16_t* const col = list + (threadIdx.x & 31);  // this lane's column: col[k * 32]
+    const f32x2 pos2 = pack2(pos);
     bool more;
     do {
         uint32_t cnt = 0;
@@ -267,8 +271,9 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
 #pragma unroll 1
             for (; c < lim; ++c) {
                 const float2 nxt = tile_pos[c + 1];
-                const float dx = S::sub(pos.x, po.x), dy = S::sub(pos.y, po.y);  // sfm.rs:131-135
-                bool ok = !(S::add(S::mul(dx, dx), S::mul(dy, dy)) > 4.0f);
+                const f32x2 dv = sub2(pos2, pack2(po));  // sfm.rs:131-135, IEEE per component
+                const float2 dd = unpack2(mul2(dv, dv));
+                bool ok = !(S::add(dd.x, dd.y) > 4.0f);
                 if (d == 1) ok = ok && (c != self);  // sfm.rs:130
                 col[cnt * 32] = static_cast<uint16_t>(c);
                 cnt += ok ? 1u : 0u;

@@ -51,6 +51,37 @@ struct Ops<Math::Fast> {
 
 using S = Ops<Math::Strict>;
 
+// ---- packed fp32x2 (sm_100: FADD2 / FMUL2 / FFMA2) ---------------------------------------------------
+// One issue slot for the x and y component of a Vec2 operation. `.rn` forms are IEEE per component,
+// i.e. bit-identical to two scalar `_rn` intrinsics — usable on the exact paths too.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ f32x2 pack2(float2 v) { return pack2(v.x, v.y); }
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Field samplers — util.rs:44-58 `bilinear`, util.rs:61-75 `sobel_filter`, field.rs:235-258.
 // Maps are row-major (y, x) f32 (ndarray Array2 of shape (fy, fx), util.rs:29-40). An out-of-bounds
