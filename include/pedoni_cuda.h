@@ -165,6 +165,20 @@ int pedoni_cell_table(PedoniModel* model, uint32_t* indices, uint32_t cap, uint3
 /* Wait for all enqueued work of this handle. */
 int pedoni_synchronize(PedoniModel* model);
 
+/* ---- field precompute on the host (the step before the path) -----------
+ *
+ * `Field::from_scenario` (field.rs:220-232): outline rasterisation of obstacles and waypoints plus the
+ * reference's fast-marching variant. Pure host code (OpenMP over the potential maps), no GPU needed.
+ * obstacles / waypoints: 5 floats each (x0, y0, x1, y1, width). Outputs are caller-allocated:
+ * obstacle_exist[fy*fx] (0/1), distance_map[fy*fx], potential_maps[n_waypoints*fy*fx], row-major (y, x),
+ * with (fy, fx) from pedoni_field_shape = ceil(size / unit) (field.rs:25-26). The arrays are exactly what
+ * PedoniConfig.distance_map / potential_maps expect.
+ */
+int pedoni_field_shape(float size_x, float size_y, float unit, int32_t* field_ny, int32_t* field_nx);
+int pedoni_field_build(float size_x, float size_y, float unit, int32_t n_obstacles, const float* obstacles,
+                       int32_t n_waypoints, const float* waypoints, uint8_t* obstacle_exist, float* distance_map,
+                       float* potential_maps);
+
 /* ---- measurement (bench.py): device-side timers on the handle's own stream ---------------------- */
 
 typedef struct PedoniKernelTimes {

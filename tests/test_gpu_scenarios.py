@@ -120,3 +120,41 @@ def test_lanes_speed_and_lane_count_match():
         cu.model.close()
     print("lanes mean speed [m/s] cuda/oracle:", _agree(sp_cu, sp_or, 0.02, "lanes mean speed"))
     print("lanes lane count cuda/oracle:", _agree(ln_cu, ln_or, 0.5, "lanes lane count"))
+
+
+def test_headless_runner_writes_the_reference_log(tmp_path):
+    """`python -m pedoni_b200 scenario.toml --headless --max-steps N` (main.rs:106-136): TOML in, JSON log out."""
+    import json
+    from pedoni_b200.__main__ import main
+    toml = tmp_path / "corridor.toml"
+    toml.write_text("""
+[field]
+size = [40, 12]
+[[waypoints]]
+line = [[3, 2], [3, 10]]
+[[waypoints]]
+line = [[37, 2], [37, 10]]
+[[obstacles]]
+line = [[0, 1], [40, 1]]
+width = 0.5
+[[obstacles]]
+line = [[0, 11], [40, 11]]
+width = 0.5
+[[pedestrians]]
+origin = 0
+destination = 1
+spawn = { kind = "periodic", frequency = 8.0 }
+[[pedestrians]]
+origin = 1
+destination = 0
+spawn = { kind = "once", count = 40 }
+""")
+    assert main([str(toml), "--headless", "--max-steps", "400", "--log-dir", str(tmp_path / "logs"), "--seed", "7"]) == 0
+    (log_file,) = list((tmp_path / "logs").glob("*_log.json"))
+    log = json.loads(log_file.read_text())
+    assert log["total_steps"] == 400 and set(log["step_metrics"]) == {
+        "active_ped_count", "time_spawn", "time_calc_state", "time_calc_state_kernel"}
+    counts = log["step_metrics"]["active_ped_count"]
+    assert len(counts) == 400 and counts[0] >= 40 and max(counts) > 40   # the "once" group, then the inflow
+    assert counts[-1] < max(counts)                                      # and people do arrive and leave
+    assert log["preprocess_metrics"]["time_calc_field"] > 0
