@@ -122,9 +122,18 @@ __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin
               l.ticket + l.idx);
 }
 
-// ---- scan: exclusive prefix over n_cells counters, three launches built from block-wide scans -----
+// ---- scan: exclusive prefix over n_cells counters in ONE pass (chained scan with decoupled look-back) --
+// A tile = 512 threads x 16 cells. Tiles are handed out by an atomic ticket (so a tile only ever waits for
+// tiles whose CTAs are already running), publish first their aggregate and then their inclusive prefix in
+// a 64-bit status word tagged with the tick (no reset between launches), and look back over their
+// predecessors for the exclusive prefix. The same pass
+//   - zeroes the counters for the next tick's fused histogram (force epilogue / key_kernel),
+//   - writes the layout ranges that depend on the owned rows (the thread that produces the cell-start
+//     they are read from writes them), and
+//   - publishes the owned population to the host: one aligned 64-bit store to pinned memory,
+//     tick << 32 | n_owned, so a lagging reader never sees a torn pair.
 constexpr int kScanThreads = 512;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;  // cells per block
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
@@ -156,60 +165,119 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* b
     return excl;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ cell_count,
-                                                                   uint32_t n_cells, uint32_t* __restrict__ tile_sums) {
-    __shared__ uint32_t total;
-    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    uint32_t sum = 0;
-    if (base + kScanItems <= n_cells) {
-        const uint4* p = reinterpret_cast<const uint4*>(cell_count + base);
-        uint4 a = p[0], b = p[1];
-        sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-    } else {
-        for (int k = 0; k < kScanItems; ++k)
-            if (base + k < n_cells) sum += cell_count[base + k];
-    }
-    block_exclusive_scan(sum, &total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+struct ScanLayout {  // what the scan publishes besides the table (see RangeId)
+    uint32_t own_begin_cell, own_end_cell, nx;
+    int has_below, has_above;
+    uint32_t* ranges;
+    unsigned long long* host_slot;
+    uint32_t tick;
+};
+
+constexpr unsigned long long kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62;
+__device__ __forceinline__ unsigned long long scan_status(unsigned long long flag, uint32_t tick, uint32_t value) {
+    return flag | (static_cast<unsigned long long>(tick & 0x3FFFFFFFu) << 32) | value;
 }
 
-// Single block: exclusive scan of the tile sums in place.
-__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(uint32_t* __restrict__ tile_sums, uint32_t n_tiles) {
-    __shared__ uint32_t total;
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < n_tiles; base += kScanThreads) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < n_tiles ? tile_sums[i] : 0u;
-        uint32_t excl = block_exclusive_scan(v, &total);
-        if (i < n_tiles) tile_sums[i] = carry + excl;
-        carry += total;
-        __syncthreads();
+__device__ __forceinline__ void publish_cell_start(const ScanLayout& L, uint32_t cell, uint32_t start) {
+    if (cell == L.own_end_cell) {  // one past the last owned agent
+        L.ranges[2 * kRangeOwned + 1] = start;
+        if (!L.has_above) {
+            L.ranges[2 * kRangeInterior + 1] = start;
+            L.ranges[2 * kRangeCompute + 1] = start;
+            L.ranges[2 * kRangeEdgeHi] = start;
+            L.ranges[2 * kRangeEdgeHi + 1] = start;
+        }
+        const uint32_t first = L.ranges[2 * kRangeOwned];  // constant: the array offset (reset_layout_kernel)
+        *L.host_slot = (static_cast<unsigned long long>(L.tick) << 32) | static_cast<unsigned long long>(start - first);
     }
+    if (L.has_below && cell == L.own_begin_cell + L.nx) L.ranges[2 * kRangeInterior] = start;
+    if (L.has_above && cell == L.own_end_cell - L.nx) L.ranges[2 * kRangeInterior + 1] = start;
 }
 
-// cell_start[c] = offset + exclusive prefix; cell_start[n_cells] = offset + total. `offset` is the
-// halo capacity H on a slab handle (owned agents start at H), 0 otherwise.
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ cell_count,
-                                                                  uint32_t n_cells,
-                                                                  const uint32_t* __restrict__ tile_sums,
-                                                                  uint32_t offset,
-                                                                  uint32_t* __restrict__ cell_start) {
-    __shared__ uint32_t total;
-    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+// cell_start[c] = offset + exclusive prefix; cell_start[n_cells] = offset + total. `offset` is the halo
+// capacity H on a slab handle with a neighbour below (owned agents start at H), 0 otherwise.
+__global__ void __launch_bounds__(kScanThreads) scan_cells_kernel(uint32_t* __restrict__ cell_count, uint32_t n_cells,
+                                                                  uint32_t offset, uint32_t* __restrict__ cell_start,
+                                                                  unsigned long long* __restrict__ tile_status,
+                                                                  uint32_t* __restrict__ tile_ticket, uint32_t n_tiles,
+                                                                  ScanLayout L) {
+    __shared__ uint32_t s_tile, s_total, s_prefix;
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(tile_ticket, 1u);
+        if (s_tile == n_tiles - 1) *tile_ticket = 0;  // every ticket of this launch has been taken
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
     uint32_t sum = 0;
+    if (base + kScanItems <= n_cells) {
+        uint4* p = reinterpret_cast<uint4*>(cell_count + base);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = (base + k < n_cells) ? cell_count[base + k] : 0u;
-        sum += v[k];
+        for (int q = 0; q < kScanItems / 4; ++q) {
+            const uint4 a = p[q];
+            v[4 * q] = a.x, v[4 * q + 1] = a.y, v[4 * q + 2] = a.z, v[4 * q + 3] = a.w;
+            p[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (base + k < n_cells) ? cell_count[base + k] : 0u;
+            if (base + k < n_cells) cell_count[base + k] = 0u;
+        }
     }
-    uint32_t run = offset + tile_sums[blockIdx.x] + block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) sum += v[k];
+    const uint32_t excl = block_exclusive_scan(sum, &s_total);
+
+    // look-back by warp 0: tile - 1, tile - 2, ... until a tile that already knows its inclusive prefix
+    if (threadIdx.x < 32) {
+        volatile unsigned long long* status = tile_status;
+        const unsigned long long tag = static_cast<unsigned long long>(L.tick & 0x3FFFFFFFu) << 32;
+        if (threadIdx.x == 0 && tile > 0) status[tile] = scan_status(kScanAggregate, L.tick, s_total);
+        uint32_t prefix = 0;
+        int look = static_cast<int>(tile) - 1 - static_cast<int>(threadIdx.x);
+        bool open = tile > 0;
+        while (open) {
+            unsigned long long st = 0;
+            if (look >= 0) {
+                do {
+                    st = status[look];
+                } while ((st & 0x3FFFFFFF00000000ull) != tag || (st >> 62) == 0);
+            } else {
+                st = kScanPrefix;  // before tile 0: prefix 0
+            }
+            const unsigned has_prefix = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
+            // lanes up to and including the first one that holds a full prefix contribute
+            const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;
+            uint32_t contrib = (static_cast<int>(threadIdx.x) <= first) ? static_cast<uint32_t>(st) : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) contrib += __shfl_down_sync(0xFFFFFFFFu, contrib, d);
+            prefix += __shfl_sync(0xFFFFFFFFu, contrib, 0);
+            open = has_prefix == 0;
+            look -= 32;
+        }
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            __threadfence();
+            status[tile] = scan_status(kScanPrefix, L.tick, prefix + s_total);
+        }
+    }
+    __syncthreads();
+
+    uint32_t run = offset + s_prefix + excl;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < n_cells) cell_start[base + k] = run;
+        if (base + k < n_cells) {
+            cell_start[base + k] = run;
+            publish_cell_start(L, base + k, run);
+        }
         run += v[k];
     }
-    if (base < n_cells && base + kScanItems >= n_cells) cell_start[n_cells] = run;
+    if (base < n_cells && base + kScanItems >= n_cells) {
+        cell_start[n_cells] = run;
+        publish_cell_start(L, n_cells, run);
+    }
 }
 
 // ---- scatter: perm[start[cell] + ticket] = t -----------------------------------------------------
@@ -245,32 +313,6 @@ __global__ void __launch_bounds__(256) gather_kernel(SortInput in, uint32_t tota
     out.vel[dst] = a.vel[idx];
     out.v0[dst] = a.v0[idx];
     out.dest[dst] = a.dest[idx];
-}
-
-// ---- layout ranges --------------------------------------------------------------------------------
-// After the scan: the ranges that depend on the owned rows only, and the owned count for the host
-// (one aligned 64-bit store to pinned memory: tick << 32 | n_owned, so a lagging reader never sees a
-// torn pair). On a handle without ghosts this also fixes the compute / edge ranges.
-__global__ void publish_layout_kernel(const uint32_t* __restrict__ cell_start, uint32_t own_begin_cell,
-                                      uint32_t own_end_cell, uint32_t nx, int has_below, int has_above,
-                                      uint32_t* __restrict__ ranges, unsigned long long* __restrict__ host_slot,
-                                      uint32_t tick) {
-    const uint32_t b = cell_start[own_begin_cell], e = cell_start[own_end_cell];
-    ranges[2 * kRangeOwned] = b;
-    ranges[2 * kRangeOwned + 1] = e;
-    ranges[2 * kRangeInterior] = has_below ? cell_start[own_begin_cell + nx] : b;
-    ranges[2 * kRangeInterior + 1] = has_above ? cell_start[own_end_cell - nx] : e;
-    if (!has_below) {
-        ranges[2 * kRangeCompute] = b;
-        ranges[2 * kRangeEdgeLo] = b;
-        ranges[2 * kRangeEdgeLo + 1] = b;
-    }
-    if (!has_above) {
-        ranges[2 * kRangeCompute + 1] = e;
-        ranges[2 * kRangeEdgeHi] = e;
-        ranges[2 * kRangeEdgeHi + 1] = e;
-    }
-    *host_slot = (static_cast<unsigned long long>(tick) << 32) | static_cast<unsigned long long>(e - b);
 }
 
 // ---- ghost rows -----------------------------------------------------------------------------------

@@ -86,9 +86,13 @@ struct PedoniModel {
     uint32_t aux_cap = 0;
     uint32_t* d_cell_count = nullptr;
     uint32_t* d_cell_start = nullptr;
-    uint32_t* d_tile_sums = nullptr;
+    unsigned long long* d_tile_status = nullptr;  // chained-scan status words (tick-tagged, never reset)
+    uint32_t* d_tile_ticket = nullptr;
     uint32_t n_tiles = 0;
-    uint32_t* d_ranges = nullptr;  // [kNumRanges][2], see RangeId
+    // [2][kNumRanges][2], see RangeId. Double-buffered: a rebuild's scan already publishes the NEXT layout
+    // while its scatter / gather still locate the sort input through the current one.
+    uint32_t* d_ranges = nullptr;
+    int rcur = 0;
     uint32_t* d_error = nullptr;
     unsigned long long* d_updates = nullptr;
     uint64_t launches = 0;  // kernels launched by this handle
@@ -126,7 +130,8 @@ struct PedoniModel {
 
     uint32_t n_sides() const { return (has_below ? 1u : 0u) + (has_above ? 1u : 0u); }
     uint32_t compute_upper() const { return owned_upper + n_sides() * halo_cap; }
-    const uint32_t* range(int id) const { return d_ranges + 2 * id; }
+    uint32_t* ranges(int which) const { return d_ranges + which * 2 * kNumRanges; }
+    const uint32_t* range(int id) const { return ranges(rcur) + 2 * id; }
 };
 
 namespace {
@@ -422,7 +427,7 @@ int check_device_error(PedoniModel* m) {
 }
 
 __global__ void reset_layout_kernel(uint32_t* ranges, uint32_t offset, unsigned long long* host_slot, uint32_t tick) {
-    for (int k = 0; k < 2 * kNumRanges; ++k) ranges[k] = offset;
+    for (int k = 0; k < 2 * 2 * kNumRanges; ++k) ranges[k] = offset;  // both layout buffers
     *host_slot = static_cast<unsigned long long>(tick) << 32;
 }
 
@@ -455,7 +460,7 @@ void enqueue_unpack(PedoniModel* m) {
     halo_unpack_kernel<<<grid, 256, 0, m->edge_stream>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell,
                                                          m->own_end_cell, m->grid.nx, m->halo_cap, m->cap,
                                                          msg_of(m->d_recv_below), msg_of(m->d_recv_above),
-                                                         m->has_below, m->has_above, m->d_ranges, m->d_error);
+                                                         m->has_below, m->has_above, m->ranges(m->rcur), m->d_error);
     m->launches += 1;
     cudaEventRecord(m->ev_halo, m->edge_stream);
     m->halo_pending = false;
@@ -640,8 +645,12 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     m->n_tiles = div_up(m->n_cells, kScanTile);
     CREATE_TRY(cudaMalloc(&m->d_cell_count, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
     CREATE_TRY(cudaMalloc(&m->d_cell_start, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
-    CREATE_TRY(cudaMalloc(&m->d_tile_sums, sizeof(uint32_t) * std::max<uint32_t>(m->n_tiles, 1)));
-    CREATE_TRY(cudaMalloc(&m->d_ranges, sizeof(uint32_t) * 2 * kNumRanges));
+    CREATE_TRY(cudaMalloc(&m->d_tile_status, sizeof(unsigned long long) * std::max<uint32_t>(m->n_tiles, 1)));
+    CREATE_TRY(cudaMemsetAsync(m->d_tile_status, 0, sizeof(unsigned long long) * std::max<uint32_t>(m->n_tiles, 1),
+                               m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_tile_ticket, sizeof(uint32_t)));
+    CREATE_TRY(cudaMemsetAsync(m->d_tile_ticket, 0, sizeof(uint32_t), m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_ranges, sizeof(uint32_t) * 2 * 2 * kNumRanges));
     CREATE_TRY(cudaMalloc(&m->d_error, sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&m->d_updates, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(m->d_updates, 0, sizeof(unsigned long long), m->stream));
@@ -681,7 +690,8 @@ void pedoni_destroy(PedoniModel* m) {
     free_agents(m->app);
     for (void* p : {(void*)m->d_keys[0], (void*)m->d_keys[1], (void*)m->d_keys_app, (void*)m->d_tickets[0], (void*)m->d_tickets[1], (void*)m->d_tickets_app,
                     (void*)m->d_perm,
-                    (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_sums, (void*)m->d_ranges,
+                    (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_status, (void*)m->d_tile_ticket,
+                    (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_distance, (void*)m->d_potential,
                     (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_recv_below,
                     (void*)m->d_recv_above})
@@ -788,15 +798,15 @@ static int rebuild_impl(PedoniModel* m) {
             m->launches += 1;
         }
     }
+    advance_tick(m, (uint64_t)m->app_n + (uint64_t)m->n_sides() * m->halo_cap);
     {
         ScopedTimer t(m, kScan, s);
-        scan_reduce_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums);
-        scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(m->d_tile_sums, m->n_tiles);
-        scan_apply_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->d_tile_sums,
-                                                              m->array_offset, m->d_cell_start);
-        // zero the counters for the next tick's fused histogram (force epilogue / key_kernel)
-        CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, s));
-        m->launches += 3;
+        ScanLayout layout{m->own_begin_cell, m->own_end_cell, static_cast<uint32_t>(m->grid.nx), m->has_below,
+                          m->has_above,     m->ranges(m->rcur ^ 1), m->h_pub_dev,               m->tick};
+        scan_cells_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->array_offset,
+                                                              m->d_cell_start, m->d_tile_status, m->d_tile_ticket,
+                                                              m->n_tiles, layout);
+        m->launches += 1;
     }
     if (total > 0) {
         {
@@ -810,12 +820,8 @@ static int rebuild_impl(PedoniModel* m) {
             m->launches += 1;
         }
     }
-    advance_tick(m, (uint64_t)m->app_n + (uint64_t)m->n_sides() * m->halo_cap);
-    publish_layout_kernel<<<1, 1, 0, s>>>(m->d_cell_start, m->own_begin_cell, m->own_end_cell, m->grid.nx,
-                                          m->has_below, m->has_above, m->d_ranges, m->h_pub_dev, m->tick);
-    m->launches += 1;
-
     m->cur ^= 1;
+    m->rcur ^= 1;  // the layout the scan published describes buf[cur] from here on
     m->owned_upper = owned_bound(m, total);
     m->app_n = 0;
     m->keys_fresh = false;
