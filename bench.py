@@ -48,8 +48,8 @@ def parse_args():
     ap.add_argument("--agents", type=int, default=10_000_000)
     ap.add_argument("--density", type=float, default=1.0)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--cpu-agents", type=int, default=400_000, help="bounded sample for the CPU baseline")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-agents", type=int, default=4_000_000, help="bounded sample for the CPU legs (~0.35 s/tick on 16 cores)")
+    ap.add_argument("--cpu-steps", type=int, default=20, help="ticks of the cpu_baseline leg (~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--relax", type=int, default=RELAX_STEPS)
@@ -121,6 +121,7 @@ def run_reference(args):
     pos, dest, vel, v0 = crowd.agents()
     m = oracle.OracleModel(sc.field.size, 1.4, field.unit, field.distance_map, field.potential_maps)
     m.spawn(pos, dest, v0)
+    oracle.lib().oracle_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = oracle.lib().oracle_max_threads()
     m.run(max(args.warmup, 1))
     t0 = time.time()
@@ -153,6 +154,7 @@ def cpu_baseline(args):
     pos, dest, vel, v0 = crowd.agents()
     m = oracle.OracleModel(sc.field.size, 1.4, field.unit, field.distance_map, field.potential_maps)
     m.spawn(pos, dest, v0)
+    oracle.lib().oracle_set_threads(os.cpu_count() or 1)
     m.run(1)
     updates, ts, tc = m.run(args.cpu_steps)
     return {"value": updates / (ts + tc), "unit": "updates/s", "cores": oracle.lib().oracle_max_threads(),
