@@ -130,6 +130,12 @@ int pedoni_step(PedoniModel* model);
 /* PedestrianModel::get_pedestrian_count (sfm.rs:267-269). Blocks. Negative = PedoniStatus. */
 int32_t pedoni_count(PedoniModel* model);
 
+/* The same without blocking: the population of the owned rows as of the most
+ * recent rebuild the DEVICE has completed, and that rebuild's ordinal. The reference reads the count after
+ * every tick (lib.rs:95), which costs a host/device synchronisation per tick; a headless loop that only
+ * logs the series can read this lagging value instead (it trails the host by the ticks still in flight). */
+int pedoni_count_published(PedoniModel* model, int32_t* count, uint32_t* rebuild_ordinal);
+
 /*
  * PedestrianModel::list_pedestrians (sfm.rs:257-265) plus the model's private columns.
  * Writes min(count, cap) agents in the model's current order; *n_out = count. pos_xy and

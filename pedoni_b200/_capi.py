@@ -72,6 +72,7 @@ SIGNATURES = {
     "pedoni_rebuild": (C.c_int, [C.c_void_p]),
     "pedoni_step": (C.c_int, [C.c_void_p]),
     "pedoni_count": (C.c_int32, [C.c_void_p]),
+    "pedoni_count_published": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), c_u32_p]),
     "pedoni_download": (C.c_int, [C.c_void_p, c_float_p, c_u32_p, c_float_p, c_float_p, C.c_uint32, c_u32_p]),
     "pedoni_download_begin": (C.c_int, [C.c_void_p, c_float_p, c_u32_p, C.c_uint32]),
     "pedoni_download_end": (C.c_int, [C.c_void_p, c_u32_p]),

@@ -967,6 +967,15 @@ int32_t pedoni_count(PedoniModel* m) {
     return static_cast<int32_t>(e - b + m->app_n);
 }
 
+// Non-blocking population: what the device last published (after the most recent COMPLETED rebuild).
+int pedoni_count_published(PedoniModel* m, int32_t* count, uint32_t* tick) {
+    if (!m || !count) return PEDONI_ERR_INVALID;
+    const unsigned long long pub = *reinterpret_cast<volatile unsigned long long*>(m->h_pub);
+    *count = static_cast<int32_t>(static_cast<uint32_t>(pub));
+    if (tick) *tick = static_cast<uint32_t>(pub >> 32);
+    return PEDONI_OK;
+}
+
 int pedoni_download(PedoniModel* m, float* pos_xy, uint32_t* dest, float* vel_xy, float* v0, uint32_t cap,
                     uint32_t* n_out) {
     if (!m) return PEDONI_ERR_INVALID;

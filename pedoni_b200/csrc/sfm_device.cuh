@@ -35,7 +35,7 @@ struct Ops<Math::Fast> {
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }  // constants fold
     static __device__ __forceinline__ float sqrt(float a) {
         float r;
         asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));

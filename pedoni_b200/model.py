@@ -107,6 +107,12 @@ class SocialForceModelCuda:
         """mod.rs:25 / sfm.rs:267-269."""
         return _capi.check(self._lib.pedoni_count(self._h), self._h)
 
+    def count_published(self):
+        """(population, rebuild ordinal) as last published by the device; never blocks."""
+        n, t = C.c_int32(), C.c_uint32()
+        _capi.check(self._lib.pedoni_count_published(self._h, C.byref(n), C.byref(t)), self._h)
+        return n.value, t.value
+
     # -- array-level entry points (what the trait methods are made of) ----------------------------
     def spawn_arrays(self, pos: np.ndarray, dest: np.ndarray, v0: np.ndarray) -> None:
         pos, v0 = _f32(pos), _f32(v0)

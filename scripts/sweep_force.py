@@ -12,16 +12,13 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-VARIANTS = {  # name: (threads, min_blocks, tile, list)
-    "t128_b9_192_32": (128, 9, 192, 32),
-    "t128_b10_192_32": (128, 10, 192, 32),
-    "t128_b11_160_32": (128, 11, 160, 32),
-    "t192_b6_192_32": (192, 6, 192, 32),
-    "t256_b4_192_32": (256, 4, 192, 32),
-    "t256_b5_192_32": (256, 5, 192, 32),
-    "t256_b5_160_32": (256, 5, 160, 32),
-    "t512_b2_192_32": (512, 2, 192, 32),
-    "t64_b18_192_32": (64, 18, 192, 32),
+VARIANTS = {  # name: extra -D flags
+    "base": [],
+    "bigcheck": ["-DPEDONI_EXP_BIGCHECK=1"],
+    "oldnorm": ["-DPEDONI_EXP_OLDNORM=1"],
+    "both_old": ["-DPEDONI_EXP_BIGCHECK=1", "-DPEDONI_EXP_OLDNORM=1"],
+    "b8": ["-DPEDONI_FORCE_MIN_BLOCKS=8"],
+    "b10_160": ["-DPEDONI_FORCE_MIN_BLOCKS=10", "-DPEDONI_TILE_ENTRIES=160"],
 }
 OUT = ROOT / "build" / "variants"
 
@@ -31,10 +28,8 @@ def main():
     if mode == "build":
         from pedoni_b200 import build as b
         OUT.mkdir(parents=True, exist_ok=True)
-        for name, (t, mb, tile, lst) in VARIANTS.items():
-            b.build(out=OUT / f"libpedoni_{name}.so",
-                    extra=[f"-DPEDONI_FORCE_THREADS={t}", f"-DPEDONI_FORCE_MIN_BLOCKS={mb}",
-                           f"-DPEDONI_TILE_ENTRIES={tile}", f"-DPEDONI_LIST_DEPTH={lst}"])
+        for name, flags in VARIANTS.items():
+            b.build(out=OUT / f"libpedoni_{name}.so", extra=flags)
             print("built", name)
     else:
         agents = sys.argv[sys.argv.index("--agents") + 1] if "--agents" in sys.argv else "10000000"

@@ -181,3 +181,21 @@ def test_pipelined_download_equals_blocking_download(corridor):
     with pytest.raises(PedoniError):
         cu.download_end()     # nothing in flight
     cu.close()
+
+
+def test_published_count_trails_but_never_blocks(corridor):
+    sc, field = corridor
+    cu, orc = helpers.make_pair(sc, field)
+    pos, dest, vel, v0 = helpers.random_crowd(2000, sc.field.size, seed=2, margin=4.0)
+    cu.upload_state(pos, dest, vel, v0)
+    seen = []
+    for _ in range(5):
+        cu.rebuild()
+        cu.step()
+        seen.append(cu.count_published())  # no synchronisation: may still show an older rebuild
+    cu.synchronize()
+    n, ordinal = cu.count_published()
+    cu.rebuild()                           # count() reports the state after this rebuild
+    assert n + 0 >= cu.get_pedestrian_count() > 0
+    assert all(a[1] <= b[1] for a, b in zip(seen, seen[1:])) and seen[-1][1] <= ordinal
+    cu.close()
