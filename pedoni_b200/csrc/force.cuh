@@ -48,6 +48,9 @@ constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0
 #ifndef PEDONI_FORCE_MIN_BLOCKS_STRICT
 #define PEDONI_FORCE_MIN_BLOCKS_STRICT 8  // the IEEE path (fp64 exp, divides) needs the registers more than the warps
 #endif
+#ifndef PEDONI_FORCE_UNROLL
+#define PEDONI_FORCE_UNROLL 2  // neighbours in flight in the FORCE loop
+#endif
 #ifndef PEDONI_TILE_ENTRIES
 #define PEDONI_TILE_ENTRIES 192
 #endif
@@ -61,6 +64,7 @@ constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0
 #define PEDONI_FAST_PAIR 1   // 0: PEDONI_MATH_FAST keeps the reference-order pair term (experiments)
 #endif
 constexpr int kForceThreads = PEDONI_FORCE_THREADS;
+constexpr int kForceUnroll = PEDONI_FORCE_UNROLL;
 constexpr int kForceWarps = kForceThreads / 32;
 constexpr int kTileEntries = PEDONI_TILE_ENTRIES;  // agents per WARP tile: 3 windows of ~(32 + 2 cells) agents (~108 at 1 ped/m^2)
 constexpr int kListDepth = PEDONI_LIST_DEPTH;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
@@ -296,7 +300,7 @@ __device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const fl
             cur[d] = c;
             more = c < stop[d];
         }
-#pragma unroll 2
+#pragma unroll kForceUnroll
         for (uint32_t k = 0; k < cnt; ++k) {
             const uint32_t c = col[k * 32];
             PairTerm<(PEDONI_FAST_PAIR ? M : Math::Strict)>::add(pos, e, tile_pos[c], tile_vel[c], acc);

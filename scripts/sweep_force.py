@@ -14,11 +14,15 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {  # name: extra -D flags
     "base": [],
-    "bigcheck": ["-DPEDONI_EXP_BIGCHECK=1"],
-    "oldnorm": ["-DPEDONI_EXP_OLDNORM=1"],
-    "both_old": ["-DPEDONI_EXP_BIGCHECK=1", "-DPEDONI_EXP_OLDNORM=1"],
-    "b8": ["-DPEDONI_FORCE_MIN_BLOCKS=8"],
-    "b10_160": ["-DPEDONI_FORCE_MIN_BLOCKS=10", "-DPEDONI_TILE_ENTRIES=160"],
+    "unroll1": ["-DPEDONI_FORCE_UNROLL=1"],
+    "unroll3": ["-DPEDONI_FORCE_UNROLL=3"],
+    "unroll4": ["-DPEDONI_FORCE_UNROLL=4"],
+    "list24": ["-DPEDONI_LIST_DEPTH=24"],
+    "list40_tile160": ["-DPEDONI_LIST_DEPTH=40", "-DPEDONI_TILE_ENTRIES=160"],
+    "tile160": ["-DPEDONI_TILE_ENTRIES=160"],
+    "tile224_list24": ["-DPEDONI_TILE_ENTRIES=224", "-DPEDONI_LIST_DEPTH=24"],
+    "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
+    "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
 OUT = ROOT / "build" / "variants"
 

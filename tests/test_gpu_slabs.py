@@ -139,3 +139,26 @@ def test_step_without_ghosts_is_refused(corridor):
     lone.close()
     with pytest.raises(PedoniError):  # 22 rows cannot give 12 slabs two rows each
         SocialForceModelCuda(SimulatorOptions(), sc, field, slab_rank=0, slab_count=12)
+
+
+def test_slabs_on_a_growing_non_uniform_crowd():
+    """bottleneck.toml (200 pedestrians/s walking in, everything funnels through one gap): the buffers of
+    every slab grow from the default capacity while ghost strips are in flight, populations are very
+    unequal between slabs, and the result must still equal the whole-domain handle bit for bit."""
+    from pedoni_b200.simulator import Simulator
+    sc = helpers.load_scenario("bottleneck")
+    opts = SimulatorOptions()
+    field = helpers.oracle_field(sc, opts.field_grid_unit)
+    whole = Simulator(opts, sc, field, SocialForceModelCuda(opts, sc, field, math_mode=PEDONI_MATH_FAST), seed=4,
+                      count_every=50)
+    slabs = Simulator(opts, sc, field, SlabGroup(opts, sc, field, 4, math_mode=PEDONI_MATH_FAST, halo_capacity=8192),
+                      seed=4, count_every=50)
+    for t in range(350):
+        mw, ms = whole.tick(), slabs.tick()
+        if (t + 1) % 50 == 0:
+            assert mw.active_ped_count == ms.active_ped_count > 0
+    _assert_same(whole.model, slabs.model)
+    per_slab = [s.get_pedestrian_count() for s in slabs.model.slabs]
+    assert max(per_slab) > 0 and sum(per_slab) == whole.model.get_pedestrian_count() > 6000
+    whole.model.close()
+    slabs.model.close()
