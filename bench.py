@@ -341,6 +341,7 @@ def run_ours(args):
                                    f"{crowd.side:.0f} m x {crowd.side:.0f} m (BASELINE.json configs[4])",
                        "density_per_m2": args.density, "neighbor_unit_m": 1.4, "field_unit_m": 0.25,
                        "math_mode": args.math, "decomposition": f"{world} row slab(s)",
+                       "slab_transport": model.slab_transport(),
                        "relax_steps_untimed": args.relax, "active_pedestrians": int(updates_all / args.steps),
                        "l2": "inputs larger than L2 (2 x 24 B x N state + 3 field maps >> 126 MB); no flush"},
             "e2e": e2e,

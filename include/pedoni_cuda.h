@@ -225,7 +225,8 @@ int pedoni_slab_rows(int32_t ny, int32_t count, int32_t rank, int32_t* row0, int
 
 #define PEDONI_COMM_ID_BYTES 128
 /* Rank 0 creates the NCCL unique id; the host program (torch.distributed, MPI, a socket) hands the
- * 128 bytes to every rank, which then joins with pedoni_comm_init (collective over the slab ranks). */
+ * 128 bytes to every rank, which then joins with pedoni_comm_init (collective over the slab ranks; call it
+ * before the first pedoni_rebuild). */
 int pedoni_comm_unique_id(void* out_id128);
 int pedoni_comm_init(PedoniModel* model, const void* id128);
 
@@ -234,6 +235,12 @@ int pedoni_comm_init(PedoniModel* model, const void* id128);
  * rows with device-to-device copies. models[i] must be slab i of n. Used where NCCL cannot be (tests
  * of the slab path on a single GPU); handles joined with pedoni_comm_init exchange by themselves. */
 int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n);
+
+/* How this handle's ghost rows travel: "peer-memory ..." (default after pedoni_comm_init when the ranks can
+ * map each other's memory through CUDA IPC: the pack kernel stores the strips straight into the
+ * neighbour over NVLink and raises a flag its unpack kernel polls; NCCL only bootstraps the handles),
+ * "nccl send/recv" (fallback, or PEDONI_SLAB_TRANSPORT=nccl), "in-process ...", or "none". */
+const char* pedoni_slab_transport(const PedoniModel* model);
 
 /* The halo capacity in effect (0 on a whole-domain handle). */
 int pedoni_halo_capacity(const PedoniModel* model, uint32_t* halo_capacity);

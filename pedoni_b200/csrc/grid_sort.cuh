@@ -339,13 +339,30 @@ struct HaloMessage {
     __host__ __device__ uint32_t* dest(uint32_t nx, uint32_t h) const { return words + halo_header_words(nx) + 5ull * h; }
 };
 
+// How a packed strip announces itself to a receiver that polls (peer-memory transport): see PeerSignal.
+struct PeerSignal {
+    uint32_t* done_count;  // local: CTAs of this pack launch that have finished a side (2 counters)
+    uint32_t* flag_down;   // in the slab BELOW's memory: its "strip from above has arrived" sequence number
+    uint32_t* flag_up;     // in the slab ABOVE's memory: its "strip from below has arrived" sequence number
+    uint32_t seq;          // ordinal of this exchange (every slab counts its rebuilds alike)
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // blockIdx.y = 0: the first two owned rows -> message for the slab below;
 // blockIdx.y = 1: the last two owned rows  -> message for the slab above.
+// `down` / `up` may point into local staging buffers (NCCL and in-process transports) or straight into
+// the neighbour's receive slot over NVLink (peer-memory transport: pack and send are this one kernel;
+// the last CTA to finish a side publishes the sequence number behind a system-wide fence).
 __global__ void __launch_bounds__(256) halo_pack_kernel(AgentArrays a, const uint32_t* __restrict__ cell_start,
                                                         uint32_t own_begin_cell, uint32_t own_end_cell, uint32_t nx,
                                                         uint32_t halo_cap, HaloMessage down, HaloMessage up,
                                                         int has_below, int has_above, uint32_t tick,
-                                                        uint32_t* __restrict__ error_flag) {
+                                                        uint32_t* __restrict__ error_flag, PeerSignal sig) {
     const int side = blockIdx.y;
     if ((side == 0 && !has_below) || (side == 1 && !has_above)) return;
     const HaloMessage msg = side == 0 ? down : up;
@@ -367,30 +384,74 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(AgentArrays a, const uin
         msg.v0(nx, halo_cap)[i] = a.v0[first + i];
         msg.dest(nx, halo_cap)[i] = a.dest[first + i];
     }
+    uint32_t* flag = side == 0 ? sig.flag_down : sig.flag_up;
+    if (flag != nullptr) {
+        __threadfence_system();  // this thread's peer stores are ordered before the signal
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t finished = atomicAdd(sig.done_count + side, 1u);
+            if (finished == gridDim.x - 1) {
+                sig.done_count[side] = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(flag) = sig.seq;
+            }
+        }
+    }
 }
 
 // blockIdx.y = 0: ghost rows r0-2, r0-1 from `below` (right-aligned to end at H);
 // blockIdx.y = 1: ghost rows r1, r1+1 from `above` (placed right after the owned agents).
 // Also completes the cell table for the ghost rows and the compute / edge ranges.
+// wait_seq != 0 (peer-memory transport): the strip is written by the neighbour's pack kernel; poll the
+// local arrival flag until it reaches this exchange's ordinal (the neighbour may already be one ahead —
+// it writes alternate slots), bounded by a time-out so that a dead peer cannot hang the GPU.
 __global__ void __launch_bounds__(256) halo_unpack_kernel(AgentArrays a, uint32_t* __restrict__ cell_start,
                                                           uint32_t own_begin_cell, uint32_t own_end_cell, uint32_t nx,
                                                           uint32_t halo_cap, uint32_t array_cap, HaloMessage below,
                                                           HaloMessage above, int has_below, int has_above,
                                                           uint32_t* __restrict__ ranges,
-                                                          uint32_t* __restrict__ error_flag) {
+                                                          uint32_t* __restrict__ error_flag,
+                                                          const uint32_t* flag_below, const uint32_t* flag_above,
+                                                          uint32_t wait_seq) {
     const int side = blockIdx.y;
     if ((side == 0 && !has_below) || (side == 1 && !has_above)) return;
     const HaloMessage msg = side == 0 ? below : above;
-    uint32_t n = msg.words[0];
-    if (n > halo_cap) n = 0;  // cannot happen with a matching sender; never index out of bounds
+    __shared__ int s_timed_out;
+    if (wait_seq != 0) {
+        if (threadIdx.x == 0) {
+            const volatile uint32_t* flag = side == 0 ? flag_below : flag_above;
+            const unsigned long long t0 = global_timer_ns();
+            int timed_out = 0;
+            while (static_cast<int32_t>(*flag - wait_seq) < 0) {
+                if (global_timer_ns() - t0 > 5000000000ull) {  // 5 s
+                    timed_out = 1;
+                    break;
+                }
+                __nanosleep(200);
+            }
+            s_timed_out = timed_out;
+            __threadfence_system();
+        }
+        __syncthreads();
+    } else if (threadIdx.x == 0) {
+        s_timed_out = 0;
+    }
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // Read the message around L1: with the peer-memory transport it was written by another GPU.
+    uint32_t n = __ldcg(msg.words);
+    if (s_timed_out) {
+        if (i == 0) atomicOr(error_flag, kErrHaloTimeout);
+        n = 0;
+    }
+    if (n > halo_cap) n = 0;  // cannot happen with a matching sender; never index out of bounds
     const uint32_t* rel = msg.starts();
     uint32_t base;
     if (side == 0) {
         base = halo_cap - n;
-        if (i < 2 * nx) cell_start[i] = base + min(rel[i], n);  // entry 2nx == own_begin_cell == H already
+        if (i < 2 * nx) cell_start[i] = base + min(__ldcg(rel + i), n);  // entry 2nx == own_begin_cell == H already
         if (i == 0) {
-            const uint32_t row_m1 = base + min(rel[nx], n);  // first agent of ghost row r0-1
+            const uint32_t row_m1 = base + min(__ldcg(rel + nx), n);  // first agent of ghost row r0-1
             ranges[2 * kRangeCompute] = row_m1;
             ranges[2 * kRangeEdgeLo] = row_m1;
             ranges[2 * kRangeEdgeLo + 1] = cell_start[own_begin_cell + nx];
@@ -401,19 +462,19 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(AgentArrays a, uint32_
             if (i == 0) atomicOr(error_flag, kErrHaloOverflow);
             n = 0;
         }
-        if (i >= 1 && i <= 2 * nx) cell_start[own_end_cell + i] = base + min(rel[i], n);
+        if (i >= 1 && i <= 2 * nx) cell_start[own_end_cell + i] = base + min(__ldcg(rel + i), n);
         if (i == 0) {
-            const uint32_t row_p1 = base + min(rel[nx], n);  // one past the last agent of ghost row r1
+            const uint32_t row_p1 = base + min(__ldcg(rel + nx), n);  // one past the last agent of ghost row r1
             ranges[2 * kRangeCompute + 1] = row_p1;
             ranges[2 * kRangeEdgeHi] = cell_start[own_end_cell - nx];
             ranges[2 * kRangeEdgeHi + 1] = row_p1;
         }
     }
     if (i < n) {
-        a.pos[base + i] = msg.pos(nx, halo_cap)[i];
-        a.vel[base + i] = msg.vel(nx, halo_cap)[i];
-        a.v0[base + i] = msg.v0(nx, halo_cap)[i];
-        a.dest[base + i] = msg.dest(nx, halo_cap)[i];
+        a.pos[base + i] = __ldcg(msg.pos(nx, halo_cap) + i);
+        a.vel[base + i] = __ldcg(msg.vel(nx, halo_cap) + i);
+        a.v0[base + i] = __ldcg(msg.v0(nx, halo_cap) + i);
+        a.dest[base + i] = __ldcg(msg.dest(nx, halo_cap) + i);
     }
 }
 

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -62,10 +63,17 @@ struct PedoniModel {
     uint32_t halo_cap = 0;     // H: capacity (agents) of one two-row ghost strip / message
     uint32_t array_offset = 0; // first owned agent sits at this index (H if has_below)
     size_t msg_bytes = 0;
-    uint32_t* d_send_dn = nullptr;     // first two owned rows, for the slab below
-    uint32_t* d_send_up = nullptr;     // last two owned rows, for the slab above
-    uint32_t* d_recv_below = nullptr;  // ghost rows r0-2, r0-1
-    uint32_t* d_recv_above = nullptr;  // ghost rows r1, r1+1
+    uint32_t* d_send_dn = nullptr;     // staging: first two owned rows, for the slab below (NCCL / in-process)
+    uint32_t* d_send_up = nullptr;     // staging: last two owned rows, for the slab above
+    // Receive arena, one allocation (one CUDA IPC handle): [control words | below slot 0 | below slot 1 |
+    // above slot 0 | above slot 1]. Exchange k uses slot k % 2, so a neighbour that is already one tick
+    // ahead never overwrites a strip that has not been unpacked yet.
+    unsigned char* d_arena = nullptr;
+    size_t arena_bytes = 0, slot_bytes = 0;
+    uint32_t exchange_seq = 0;         // rebuilds that exchanged ghosts so far (identical on every slab)
+    enum Transport { kTransportNone = 0, kTransportNccl, kTransportPeer } transport = kTransportNone;
+    unsigned char* peer_arena_below = nullptr;  // the arenas of slab rank-1 / rank+1, mapped through CUDA IPC
+    unsigned char* peer_arena_above = nullptr;
     pedoni::SlabComm* comm = nullptr;
     bool halo_pending = false;   // rebuilt, ghosts not exchanged yet (in-process transport)
     bool halo_inflight = false;  // exchange enqueued on edge_stream, main has not waited on ev_halo
@@ -128,6 +136,17 @@ struct PedoniModel {
 
     std::string last_error;
 
+    // arena layout
+    static constexpr size_t kArenaControlBytes = 256;  // [0] flag_below, [1] flag_above, [4..5] pack counters
+    uint32_t* flag_below(unsigned char* arena) const { return reinterpret_cast<uint32_t*>(arena); }
+    uint32_t* flag_above(unsigned char* arena) const { return reinterpret_cast<uint32_t*>(arena) + 1; }
+    uint32_t* pack_counters() const { return reinterpret_cast<uint32_t*>(d_arena) + 4; }
+    uint32_t* recv_below(unsigned char* arena, uint32_t slot) const {
+        return reinterpret_cast<uint32_t*>(arena + kArenaControlBytes + slot * slot_bytes);
+    }
+    uint32_t* recv_above(unsigned char* arena, uint32_t slot) const {
+        return reinterpret_cast<uint32_t*>(arena + kArenaControlBytes + (2 + slot) * slot_bytes);
+    }
     uint32_t n_sides() const { return (has_below ? 1u : 0u) + (has_above ? 1u : 0u); }
     uint32_t compute_upper() const { return owned_upper + n_sides() * halo_cap; }
     uint32_t* ranges(int which) const { return d_ranges + which * 2 * kNumRanges; }
@@ -420,6 +439,10 @@ int check_device_error(PedoniModel* m) {
         return fail(m, PEDONI_ERR_CAPACITY,
                     "two boundary rows of a slab hold more than halo_capacity = %u agents (or the ghost strip "
                     "overran the arrays); raise PedoniConfig.halo_capacity", m->halo_cap);
+    if (bits & kErrHaloTimeout)
+        return fail(m, PEDONI_ERR_COMM,
+                    "slab %d of %d waited 5 s for a neighbour's ghost strip (peer-memory transport): a rank died or "
+                    "the ranks do not call pedoni_rebuild in lockstep", m->slab_rank, m->slab_count);
     return fail(m, PEDONI_ERR_STATE,
                 "a pedestrian crossed two or more neighbor-grid rows in one step; the slab decomposition "
                 "exchanges two ghost rows per tick and cannot follow it (speed > %.1f m/s)",
@@ -453,14 +476,17 @@ void advance_tick(PedoniModel* m, uint64_t inflow) {
 
 HaloMessage msg_of(uint32_t* words) { return HaloMessage{words}; }
 
-// Enqueue the ghost unpack (edge stream) once both strips have landed in d_recv_*.
+// Enqueue the ghost unpack (edge stream). NCCL / in-process transports: the strips have landed in this
+// exchange's receive slots (stream order). Peer-memory transport: the kernel polls the arrival flags.
 void enqueue_unpack(PedoniModel* m) {
     const uint32_t threads = std::max<uint32_t>(m->halo_cap, 2 * m->grid.nx + 1);
+    const uint32_t slot = m->exchange_seq & 1u;
     dim3 grid(div_up(threads, 256), 2);
-    halo_unpack_kernel<<<grid, 256, 0, m->edge_stream>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell,
-                                                         m->own_end_cell, m->grid.nx, m->halo_cap, m->cap,
-                                                         msg_of(m->d_recv_below), msg_of(m->d_recv_above),
-                                                         m->has_below, m->has_above, m->ranges(m->rcur), m->d_error);
+    halo_unpack_kernel<<<grid, 256, 0, m->edge_stream>>>(
+        m->buf[m->cur], m->d_cell_start, m->own_begin_cell, m->own_end_cell, m->grid.nx, m->halo_cap, m->cap,
+        msg_of(m->recv_below(m->d_arena, slot)), msg_of(m->recv_above(m->d_arena, slot)), m->has_below, m->has_above,
+        m->ranges(m->rcur), m->d_error, m->flag_below(m->d_arena), m->flag_above(m->d_arena),
+        m->transport == PedoniModel::kTransportPeer ? m->exchange_seq : 0u);
     m->launches += 1;
     cudaEventRecord(m->ev_halo, m->edge_stream);
     m->halo_pending = false;
@@ -471,10 +497,69 @@ int exchange_nccl(PedoniModel* m) {
     CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, m->ev_packed, 0));
     ScopedTimer t(m, kComm, m->edge_stream);
     std::string err;
-    int rc = pedoni::slab_comm_exchange(m->comm, m->edge_stream, m->d_send_dn, m->d_recv_below, m->d_send_up,
-                                        m->d_recv_above, m->msg_bytes, m->has_below, m->has_above, &err);
+    const uint32_t slot = m->exchange_seq & 1u;
+    int rc = pedoni::slab_comm_exchange(m->comm, m->edge_stream, m->d_send_dn, m->recv_below(m->d_arena, slot),
+                                        m->d_send_up, m->recv_above(m->d_arena, slot), m->msg_bytes, m->has_below,
+                                        m->has_above, &err);
     if (rc != PEDONI_OK) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
     enqueue_unpack(m);
+    return PEDONI_OK;
+}
+
+// Peer-memory transport: nothing to enqueue but the unpack, which polls for the neighbours' strips.
+int exchange_peer(PedoniModel* m) {
+    CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, m->ev_packed, 0));  // the ghost rows go next to the new table
+    ScopedTimer t(m, kComm, m->edge_stream);
+    enqueue_unpack(m);
+    return PEDONI_OK;
+}
+
+// Map the neighbours' receive arenas (CUDA IPC) so that the pack kernel can store into them over NVLink.
+// The 64-byte handles travel through the NCCL communicator; every rank must succeed or all stay on NCCL.
+int setup_peer_transport(PedoniModel* m) {
+    const char* forced = std::getenv("PEDONI_SLAB_TRANSPORT");
+    int ok = !(forced && std::string(forced) == "nccl");
+    unsigned char* d_handles = nullptr;  // [mine | from below | from above], 64 bytes each
+    int* d_ok = nullptr;
+    cudaIpcMemHandle_t mine{}, from_below{}, from_above{};
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(m, cudaMalloc(&d_handles, 3 * 64));
+    CUDA_TRY(m, cudaMalloc(&d_ok, sizeof(int)));
+    if (ok && cudaIpcGetMemHandle(&mine, m->d_arena) != cudaSuccess) {
+        ok = 0;
+        (void)cudaGetLastError();
+    }
+    CUDA_TRY(m, cudaMemcpyAsync(d_handles, &mine, 64, cudaMemcpyHostToDevice, m->edge_stream));
+    std::string err;
+    // my handle goes to both neighbours; theirs come back (same pattern as a ghost exchange)
+    int rc = pedoni::slab_comm_exchange(m->comm, m->edge_stream, d_handles, d_handles + 64, d_handles, d_handles + 128, 64,
+                                        m->has_below, m->has_above, &err);
+    if (rc != PEDONI_OK) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
+    CUDA_TRY(m, cudaMemcpyAsync(&from_below, d_handles + 64, 64, cudaMemcpyDeviceToHost, m->edge_stream));
+    CUDA_TRY(m, cudaMemcpyAsync(&from_above, d_handles + 128, 64, cudaMemcpyDeviceToHost, m->edge_stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->edge_stream));
+    void* p = nullptr;
+    if (ok && m->has_below) {
+        if (cudaIpcOpenMemHandle(&p, from_below, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
+            m->peer_arena_below = static_cast<unsigned char*>(p);
+        else
+            ok = 0;
+    }
+    if (ok && m->has_above) {
+        if (cudaIpcOpenMemHandle(&p, from_above, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
+            m->peer_arena_above = static_cast<unsigned char*>(p);
+        else
+            ok = 0;
+    }
+    (void)cudaGetLastError();
+    CUDA_TRY(m, cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, m->edge_stream));
+    rc = pedoni::slab_comm_all_min(m->comm, m->edge_stream, d_ok, &err);
+    if (rc != PEDONI_OK) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
+    CUDA_TRY(m, cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, m->edge_stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->edge_stream));
+    cudaFree(d_handles);
+    cudaFree(d_ok);
+    m->transport = ok ? PedoniModel::kTransportPeer : PedoniModel::kTransportNccl;
     return PEDONI_OK;
 }
 
@@ -603,10 +688,14 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
         int prio_least = 0, prio_greatest = 0;
         CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         CREATE_TRY(cudaStreamCreateWithPriority(&m->edge_stream, cudaStreamNonBlocking, prio_greatest));
-        for (uint32_t** b : {&m->d_send_dn, &m->d_send_up, &m->d_recv_below, &m->d_recv_above}) {
+        for (uint32_t** b : {&m->d_send_dn, &m->d_send_up}) {
             CREATE_TRY(cudaMalloc(b, m->msg_bytes));
             CREATE_TRY(cudaMemsetAsync(*b, 0, m->msg_bytes, m->stream));
         }
+        m->slot_bytes = (m->msg_bytes + 255) & ~static_cast<size_t>(255);
+        m->arena_bytes = PedoniModel::kArenaControlBytes + 4 * m->slot_bytes;
+        CREATE_TRY(cudaMalloc(&m->d_arena, m->arena_bytes));
+        CREATE_TRY(cudaMemsetAsync(m->d_arena, 0, m->arena_bytes, m->stream));
         for (cudaEvent_t* e : {&m->ev_packed, &m->ev_halo, &m->ev_edge, &m->ev_peer})
             CREATE_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
@@ -677,6 +766,8 @@ void pedoni_destroy(PedoniModel* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->edge_stream) cudaStreamSynchronize(m->edge_stream);
+    if (m->peer_arena_below) cudaIpcCloseMemHandle(m->peer_arena_below);
+    if (m->peer_arena_above) cudaIpcCloseMemHandle(m->peer_arena_above);
     if (m->comm) pedoni::slab_comm_destroy(m->comm);
     for (auto& t : m->timed) {
         cudaEventDestroy(t.start);
@@ -693,8 +784,7 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_status, (void*)m->d_tile_ticket,
                     (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_distance, (void*)m->d_potential,
-                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_recv_below,
-                    (void*)m->d_recv_above})
+                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
     if (m->dl_stream) {
@@ -831,16 +921,32 @@ static int rebuild_impl(PedoniModel* m) {
     if (m->slab_count > 1) {
         const uint32_t threads = std::max<uint32_t>(m->halo_cap, 2 * m->grid.nx + 1);
         dim3 grid(div_up(threads, 256), 2);
+        m->exchange_seq += 1;
+        const uint32_t slot = m->exchange_seq & 1u;
+        HaloMessage down = msg_of(m->d_send_dn), up = msg_of(m->d_send_up);
+        PeerSignal sig{m->pack_counters(), nullptr, nullptr, m->exchange_seq};
+        if (m->transport == PedoniModel::kTransportPeer) {
+            // pack + send in one kernel: my first rows are the slab below's strip "from above", and vice versa
+            if (m->has_below) {
+                down = msg_of(m->recv_above(m->peer_arena_below, slot));
+                sig.flag_down = m->flag_above(m->peer_arena_below);
+            }
+            if (m->has_above) {
+                up = msg_of(m->recv_below(m->peer_arena_above, slot));
+                sig.flag_up = m->flag_below(m->peer_arena_above);
+            }
+        }
         halo_pack_kernel<<<grid, 256, 0, s>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell, m->own_end_cell,
-                                              m->grid.nx, m->halo_cap, msg_of(m->d_send_dn), msg_of(m->d_send_up),
-                                              m->has_below, m->has_above, m->tick, m->d_error);
+                                              m->grid.nx, m->halo_cap, down, up, m->has_below, m->has_above, m->tick,
+                                              m->d_error, sig);
         m->launches += 1;
         CUDA_TRY(m, cudaEventRecord(m->ev_packed, s));
         m->halo_pending = true;
-        if (m->comm) {
+        if (m->transport == PedoniModel::kTransportPeer)
+            rc = exchange_peer(m);
+        else if (m->transport == PedoniModel::kTransportNccl)
             rc = exchange_nccl(m);
-            if (rc != PEDONI_OK) return rc;
-        }
+        if (rc != PEDONI_OK) return rc;
     }
     CUDA_TRY(m, cudaGetLastError());
     return PEDONI_OK;
@@ -872,8 +978,10 @@ static int slab_exchange_local_impl(PedoniModel* const* models, int32_t n) {
         if (m->slab_count != n || m->slab_rank != i)
             return fail(m, PEDONI_ERR_INVALID, "models[%d] is slab %d of %d, expected %d of %d", i, m->slab_rank,
                         m->slab_count, i, n);
-        if (m->comm) return fail(m, PEDONI_ERR_STATE, "handle exchanges over NCCL; the in-process transport is for "
+        if (m->comm) return fail(m, PEDONI_ERR_STATE, "handle exchanges by itself; the in-process transport is for "
                                                        "handles without pedoni_comm_init");
+        if (models[0]->exchange_seq != m->exchange_seq)
+            return fail(m, PEDONI_ERR_STATE, "slabs of one group must be rebuilt in lockstep");
         if (n > 1 && !m->halo_pending) return fail(m, PEDONI_ERR_STATE, "no rebuild pending an exchange");
         if (i > 0 && (models[i - 1]->msg_bytes != m->msg_bytes))
             return fail(m, PEDONI_ERR_INVALID, "slabs disagree on the halo message size (halo_capacity)");
@@ -887,12 +995,14 @@ static int slab_exchange_local_impl(PedoniModel* const* models, int32_t n) {
         if (m->has_below) {
             PedoniModel* o = models[i - 1];
             CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, o->ev_packed, 0));
-            CUDA_TRY(m, cudaMemcpyAsync(m->d_recv_below, o->d_send_up, m->msg_bytes, cudaMemcpyDefault, m->edge_stream));
+            CUDA_TRY(m, cudaMemcpyAsync(m->recv_below(m->d_arena, m->exchange_seq & 1u), o->d_send_up, m->msg_bytes,
+                                        cudaMemcpyDefault, m->edge_stream));
         }
         if (m->has_above) {
             PedoniModel* o = models[i + 1];
             CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, o->ev_packed, 0));
-            CUDA_TRY(m, cudaMemcpyAsync(m->d_recv_above, o->d_send_dn, m->msg_bytes, cudaMemcpyDefault, m->edge_stream));
+            CUDA_TRY(m, cudaMemcpyAsync(m->recv_above(m->d_arena, m->exchange_seq & 1u), o->d_send_dn, m->msg_bytes,
+                                        cudaMemcpyDefault, m->edge_stream));
         }
         CUDA_TRY(m, cudaEventRecord(m->ev_peer, m->edge_stream));
     }
@@ -1185,10 +1295,19 @@ int pedoni_comm_init(PedoniModel* m, const void* id128) {
     if (m->slab_count <= 1) return fail(m, PEDONI_ERR_STATE, "pedoni_comm_init on a whole-domain handle");
     if (m->comm) return fail(m, PEDONI_ERR_STATE, "communicator already initialised");
     std::string err;
+    if (m->exchange_seq != 0)
+        return fail(m, PEDONI_ERR_STATE, "join the ranks with pedoni_comm_init before the first pedoni_rebuild");
     m->comm = pedoni::slab_comm_create(id128, m->slab_rank, m->slab_count, &err);
     if (!m->comm) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
-    if (m->halo_pending) return exchange_nccl(m);  // a rebuild was already waiting for its ghosts
-    return PEDONI_OK;
+    return setup_peer_transport(m);
+}
+const char* pedoni_slab_transport(const PedoniModel* m) {
+    if (!m || m->slab_count <= 1) return "none";
+    switch (m->transport) {
+        case PedoniModel::kTransportPeer: return "peer-memory (CUDA IPC over NVLink; pack kernel stores into the neighbour)";
+        case PedoniModel::kTransportNccl: return "nccl send/recv";
+        default: return "in-process (pedoni_slab_exchange_local)";
+    }
 }
 int pedoni_halo_capacity(const PedoniModel* m, uint32_t* halo_capacity) {
     if (!m || !halo_capacity) return PEDONI_ERR_INVALID;

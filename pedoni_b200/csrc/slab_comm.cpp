@@ -6,6 +6,10 @@
 // each (grid_sort.cuh HaloMessage) inside a single ncclGroup, on the handle's edge stream, so the
 // exchange overlaps the interior force kernel running on the main stream.
 //
+// NCCL is also the bootstrap of the faster peer-memory transport (pedoni_cuda.cu, setup_peer_transport):
+// the ranks swap CUDA IPC handles of their receive arenas through this communicator; after that the pack
+// kernel stores the strips straight into the neighbour's memory and NCCL leaves the per-tick path.
+//
 // libnccl is resolved at run time (dlopen): a whole-domain user never needs it, and inside a torch
 // process the already-loaded bundled libnccl.so.2 is the one that gets used.
 #include "slab_comm.hpp"
@@ -31,6 +35,7 @@ struct NcclApi {
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
 };
 
@@ -61,6 +66,7 @@ NcclApi* load_api(std::string* err) {
             RESOLVE(Recv)
             RESOLVE(GroupStart)
             RESOLVE(GroupEnd)
+            RESOLVE(AllReduce)
             RESOLVE(GetErrorString)
 #undef RESOLVE
         }
@@ -131,6 +137,15 @@ int slab_comm_exchange(SlabComm* c, cudaStream_t stream, const void* send_dn, vo
     if (r == ncclSuccess) r = e;
     if (r != ncclSuccess) {
         if (err) *err = std::string("NCCL halo exchange: ") + a->GetErrorString(r);
+        return PEDONI_ERR_COMM;
+    }
+    return PEDONI_OK;
+}
+
+int slab_comm_all_min(SlabComm* c, cudaStream_t stream, int* d_value, std::string* err) {
+    ncclResult_t r = c->api->AllReduce(d_value, d_value, 1, ncclInt32, ncclMin, c->comm, stream);
+    if (r != ncclSuccess) {
+        if (err) *err = std::string("ncclAllReduce: ") + c->api->GetErrorString(r);
         return PEDONI_ERR_COMM;
     }
     return PEDONI_OK;

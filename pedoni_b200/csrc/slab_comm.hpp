@@ -20,4 +20,7 @@ void slab_comm_destroy(SlabComm* c);
 int slab_comm_exchange(SlabComm* c, cudaStream_t stream, const void* send_dn, void* recv_below, const void* send_up,
                        void* recv_above, size_t bytes, bool has_below, bool has_above, std::string* err);
 
+// Minimum over all slab ranks of a device-resident int32 (agreement on the transport). Enqueued on `stream`.
+int slab_comm_all_min(SlabComm* c, cudaStream_t stream, int* d_value, std::string* err);
+
 }  // namespace pedoni

@@ -209,6 +209,9 @@ class SocialForceModelCuda:
         buf = C.create_string_buffer(unique_id, _capi.PEDONI_COMM_ID_BYTES)
         _capi.check(self._lib.pedoni_comm_init(self._h, buf), self._h)
 
+    def slab_transport(self) -> str:
+        return self._lib.pedoni_slab_transport(self._h).decode()
+
     def halo_capacity(self) -> int:
         h = C.c_uint32()
         _capi.check(self._lib.pedoni_halo_capacity(self._h, C.byref(h)), self._h)

@@ -31,6 +31,7 @@ def main():
     uid = [pb.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     slab.comm_init(uid[0])
+    transport = slab.slab_transport()
     slab.upload_state(pos, dest, vel, v0)
     slab.rebuild()
     n0 = slab.get_pedestrian_count()
@@ -62,7 +63,7 @@ def main():
             base += int(t[-1])
         ok = ok and (np.concatenate(stitched) == whole.cell_table()).all()
         migrated = [p[2] for p in parts] != [len(p[0][1]) for p in parts]
-        print(f"NCCL-SLABS {'OK' if ok and migrated else 'MISMATCH'} world={world} n={len(wd)} "
+        print(f"NCCL-SLABS {'OK' if ok and migrated else 'MISMATCH'} world={world} n={len(wd)} transport={transport!r} "
               f"owned_before={[p[2] for p in parts]} owned_after={[len(p[0][1]) for p in parts]}", flush=True)
         ok = ok and migrated
     slab.close()

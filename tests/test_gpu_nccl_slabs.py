@@ -16,12 +16,20 @@ def _gpus():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_slabs_equal_whole_domain(world):
+def test_multi_gpu_slabs_equal_whole_domain(world, transport):
+    """transport = peer: strips stored into the neighbour's memory by the pack kernel (CUDA IPC over NVLink,
+    the default); nccl: grouped ncclSend/ncclRecv (the fallback, forced with PEDONI_SLAB_TRANSPORT=nccl)."""
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    import os
+    env = dict(os.environ)
+    if transport == "nccl":
+        env["PEDONI_SLAB_TRANSPORT"] = "nccl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + (10 if transport == "nccl" else 0)),
            str(ROOT / "tests" / "nccl_slab_worker.py"), "400000", "25"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "NCCL-SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert ("peer-memory" if transport == "peer" else "nccl send/recv") in r.stdout, r.stdout[-500:]
