@@ -188,7 +188,10 @@ int pedoni_field_build(float size_x, float size_y, float unit, int32_t n_obstacl
 /* ---- measurement (bench.py): device-side timers on the handle's own stream ---------------------- */
 
 typedef struct PedoniKernelTimes {
-    /* accumulated since pedoni_profile_reset, milliseconds, measured with CUDA events */
+    /* accumulated since pedoni_profile_reset, milliseconds, measured with CUDA events.
+     * key = key_kernel (spawned / uploaded agents only); histogram = 0 (the per-cell count is fused into the
+     * force epilogue and key_kernel; kept for ABI stability); scan = the single-pass chained scan;
+     * force = interior + edge launches; comm = exchange + unpack on the edge stream (overlaps force). */
     double key_ms, histogram_ms, scan_ms, scatter_ms, gather_ms, force_ms, comm_ms;
     uint64_t key_launches, histogram_launches, scan_launches, scatter_launches, gather_launches,
         force_launches, comm_launches;

@@ -1,14 +1,19 @@
 // pedoni_cuda.cu — C ABI (include/pedoni_cuda.h) over the sm_100a kernels in grid_sort.cuh and
-// force.cuh. One PedoniModel = the reference's `SocialForceModel` (sfm.rs:18-24) living on one GPU.
+// force.cuh. One PedoniModel = the reference's `SocialForceModel` (sfm.rs:18-24) living on one GPU,
+// or one row slab of it.
 //
 // Data layout in HBM (all SoA, coalesced):
 //   two agent buffers buf[0/1], each {pos float2[cap], vel float2[cap], v0 float[cap], dest u32[cap]}
-//   = 24 B/agent/buffer, the reference's PedestrianVec (sfm.rs:26-33). `cur` holds the live state;
-//   rebuild sorts cur(+appended spawns) -> other, step integrates cur -> other; both swap.
-//   keys/ticket/perm u32[cap] sort scratch; cell_count/cell_start u32[cells+1] (neighbor_grid_indices).
+//   = 24 B/agent/buffer, the reference's PedestrianVec (sfm.rs:26-33), plus keys / tickets u32[cap] per
+//   buffer (the next rebuild's cell key and in-cell slot, written by the force epilogue). `cur` holds
+//   the live state; rebuild sorts cur (+ appended spawns) -> other, step integrates cur -> other; both
+//   swap. perm u32[n] sort scratch; cell_count / cell_start u32[cells + 1] (neighbor_grid_indices).
 //   Field maps f32 row-major (field.rs:194-205), uploaded once.
-// Populations stay on the device (d_cur_range); the host only tracks upper bounds for grid sizes,
-// so spawn/rebuild/step never synchronise. count/download block.
+// Streams: `stream` (rebuild, interior force), `edge_stream` (slab handles, highest priority: ghost
+//   exchange / unpack / force on the rows next to a slab boundary), `dl_stream` (pipelined download).
+// Populations stay on the device (d_ranges, double-buffered with the layout); the host only tracks
+//   upper bounds for grid sizes, refreshed from a pinned word the scan publishes, so spawn / rebuild /
+//   step never synchronise. count / download / cell_table block.
 #include <cuda_runtime.h>
 
 #include <algorithm>
