@@ -116,6 +116,26 @@ int pedoni_spawn(PedoniModel* model, uint32_t n, const float* pos_xy, const uint
                  const float* desired_speed);
 
 /*
+ * The same append, with the pedestrians DRAWN ON THE DEVICE: what
+ * Simulator::new / Simulator::tick do before calling the plugin (lib.rs:37-52, 67-86) — for every spawn
+ * group `count` positions p1.lerp(p2, u) on the origin waypoint's line and a desired speed
+ * N(1.34, 0.26) per pedestrian (sfm.rs:54) — without a host-to-device copy of the arrays.
+ * The draws come from the counter-based stream of pedoni_b200/simulator.py `SpawnStream`
+ * (u64 number k of the stream = splitmix64(seed ^ k * 0x2545F4914F6CDD1D)): u for pedestrian j of the
+ * call is u64 number counter + j (top 24 bits), the speed's two u64 are numbers counter + n + j and
+ * counter + 2n + j, n = the sum of the counts — bit for bit what SpawnStream.f32 / .normal_approx return,
+ * so a host-drawn and a device-drawn run are identical. The per-group counts stay with the caller (the
+ * reference's Poisson draw, util.rs:78-89, is a scalar loop). Consumes 3n stream numbers.
+ */
+typedef struct PedoniSpawnGroup {
+    float p1_x, p1_y, p2_x, p2_y; /* Scenario.waypoints[origin].line */
+    uint32_t destination;
+    uint32_t count;
+} PedoniSpawnGroup;
+int pedoni_spawn_groups(PedoniModel* model, uint32_t n_groups, const PedoniSpawnGroup* groups, uint64_t seed,
+                        uint64_t counter);
+
+/*
  * PedestrianModel::spawn_pedestrians, second half (sfm.rs:58-77): neighbor-grid rebuild.
  * Cell key = trunc(pos / unit) (neighbor_grid.rs:27), out-of-grid agents are dropped
  * (neighbor_grid.rs:29), agents with potential <= 0.25 are despawned (sfm.rs:69), survivors are

@@ -32,6 +32,8 @@ def parse_args(argv=None):
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--log-dir", default="logs")
+    ap.add_argument("--device-spawn", action="store_true",
+                    help="draw spawn positions / desired speeds on the device (pedoni_spawn_groups); same run, no upload")
     ap.add_argument("--count-every", type=int, default=1, help="read the population back every N ticks (1 = reference behaviour)")
     return ap.parse_args(argv)
 
@@ -49,7 +51,8 @@ def main(argv=None) -> int:
     time_calc_field = time.perf_counter() - t0
     model = SocialForceModelCuda(opts, scenario, field, device=args.device,
                                  math_mode=PEDONI_MATH_FAST if args.math == "fast" else PEDONI_MATH_STRICT)
-    sim = Simulator(opts, scenario, field, model, seed=args.seed, count_every=args.count_every)
+    sim = Simulator(opts, scenario, field, model, seed=args.seed, count_every=args.count_every,
+                    device_spawn=args.device_spawn)
     stop = {"now": False}
     signal.signal(signal.SIGINT, lambda *_: stop.__setitem__("now", True))   # main.rs:108
     log = StepMetricsCollection()

@@ -54,6 +54,11 @@ class PedoniConfig(C.Structure):
     ]
 
 
+class PedoniSpawnGroup(C.Structure):
+    _fields_ = [("p1_x", C.c_float), ("p1_y", C.c_float), ("p2_x", C.c_float), ("p2_y", C.c_float),
+                ("destination", C.c_uint32), ("count", C.c_uint32)]
+
+
 class PedoniKernelTimes(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("key_ms", "histogram_ms", "scan_ms", "scatter_ms", "gather_ms", "force_ms", "comm_ms")] + \
@@ -69,6 +74,7 @@ SIGNATURES = {
     "pedoni_destroy": (None, [C.c_void_p]),
     "pedoni_last_error": (C.c_char_p, [C.c_void_p]),
     "pedoni_spawn": (C.c_int, [C.c_void_p, C.c_uint32, c_float_p, c_u32_p, c_float_p]),
+    "pedoni_spawn_groups": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PedoniSpawnGroup), C.c_uint64, C.c_uint64]),
     "pedoni_rebuild": (C.c_int, [C.c_void_p]),
     "pedoni_step": (C.c_int, [C.c_void_p]),
     "pedoni_count": (C.c_int32, [C.c_void_p]),

@@ -101,6 +101,49 @@ __device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
     return r;
 }
 
+// ---- device-side spawning (lib.rs:37-52,67-86; sfm.rs:49-56) with the harness's counter-based stream -----
+__host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
+    unsigned long long z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned long long spawn_stream_u64(unsigned long long seed, unsigned long long k) {
+    return splitmix64(seed ^ (k * 0x2545F4914F6CDD1Dull));
+}
+
+struct SpawnGroupDev {
+    float p1_x, p1_y, p2_x, p2_y;
+    uint32_t destination;
+    uint32_t first;  // exclusive prefix of the counts
+};
+
+// One thread per spawned pedestrian j of the call (n in total): written at out[at + j].
+__global__ void __launch_bounds__(256) spawn_groups_kernel(AgentArrays out, uint32_t at, uint32_t n,
+                                                           const SpawnGroupDev* __restrict__ groups, uint32_t n_groups,
+                                                           unsigned long long seed, unsigned long long counter) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t g = 0;  // groups are few (one per [[pedestrians]] entry): linear search
+    while (g + 1 < n_groups && groups[g + 1].first <= j) ++g;
+    const SpawnGroupDev G = groups[g];
+    // fastrand::f32(): 24 random mantissa bits
+    const float u = static_cast<float>(spawn_stream_u64(seed, counter + j) >> 40) * (1.0f / 16777216.0f);
+    // glam lerp: self + (rhs - self) * s
+    const float px = S::add(G.p1_x, S::mul(S::sub(G.p2_x, G.p1_x), u));
+    const float py = S::add(G.p1_y, S::mul(S::sub(G.p2_y, G.p1_y), u));
+    // f32_normal_approx: popcount of 64 bits centred + difference of two 32-bit uniforms, unit variance
+    const unsigned long long a = spawn_stream_u64(seed, counter + n + j), b = spawn_stream_u64(seed, counter + 2ull * n + j);
+    const double pop = static_cast<double>(__popcll(a)) - 32.0;
+    const double tri = (static_cast<double>(b & 0xFFFFFFFFull) - static_cast<double>(b >> 32)) * (1.0 / 4294967296.0);
+    const double z = (pop + tri) * 0x1.fd5a9eebfd779p-3;  // 1 / sqrt(16 + 1/6) = 0.24870800168690346
+    const float v0 = S::add(1.34f, S::mul(0.26f, static_cast<float>(z)));
+    out.pos[at + j] = make_float2(px, py);
+    out.vel[at + j] = make_float2(0.0f, 0.0f);  // sfm.rs:53
+    out.v0[at + j] = v0;
+    out.dest[at + j] = G.destination;
+}
+
 // Key + population count of one agent: shared by key_kernel and the force kernel's epilogue.
 __device__ __forceinline__ void count_key(uint32_t key, uint32_t* __restrict__ cell_count, uint32_t* key_slot,
                                           uint32_t* ticket_slot) {

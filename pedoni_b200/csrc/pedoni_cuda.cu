@@ -93,6 +93,8 @@ struct PedoniModel {
     AgentArrays app{};         // appended spawns, not yet rebuilt
     uint32_t* d_keys_app = nullptr;
     uint32_t* d_tickets_app = nullptr;
+    void* d_spawn_groups = nullptr;  // SpawnGroupDev table of pedoni_spawn_groups
+    uint32_t spawn_groups_cap = 0;
     uint32_t app_cap = 0, app_n = 0;
 
     uint32_t* d_perm = nullptr;
@@ -789,7 +791,7 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_status, (void*)m->d_tile_ticket,
                     (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_distance, (void*)m->d_potential,
-                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena})
+                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena, m->d_spawn_groups})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
     if (m->dl_stream) {
@@ -847,6 +849,42 @@ int pedoni_spawn(PedoniModel* m, uint32_t n, const float* pos_xy, const uint32_t
     if (!m) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
     return append_agents(m, n, pos_xy, dest, nullptr, v0);
+}
+
+int pedoni_spawn_groups(PedoniModel* m, uint32_t n_groups, const PedoniSpawnGroup* groups, uint64_t seed,
+                        uint64_t counter) {
+    if (!m || (n_groups > 0 && !groups)) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    std::vector<SpawnGroupDev> dev;
+    uint64_t n = 0;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        if (groups[g].count == 0) continue;
+        dev.push_back(SpawnGroupDev{groups[g].p1_x, groups[g].p1_y, groups[g].p2_x, groups[g].p2_y, groups[g].destination,
+                                    static_cast<uint32_t>(n)});
+        n += groups[g].count;
+    }
+    if (n == 0) return PEDONI_OK;
+    if ((uint64_t)m->array_offset + m->compute_upper() + m->app_n + n + m->halo_cap > 0xFFFFFFF0ull)
+        return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
+    int rc = ensure_app_capacity(m, m->app_n + static_cast<uint32_t>(n));
+    if (rc != PEDONI_OK) return rc;
+    if (dev.size() > m->spawn_groups_cap) {
+        cudaFree(m->d_spawn_groups);
+        m->d_spawn_groups = nullptr;
+        m->spawn_groups_cap = static_cast<uint32_t>(std::max<size_t>(dev.size(), 64));
+        CUDA_TRY(m, cudaMalloc(&m->d_spawn_groups, sizeof(SpawnGroupDev) * m->spawn_groups_cap));
+    }
+    // the group table is a few dozen bytes: a pageable copy is staged before the call returns
+    CUDA_TRY(m, cudaMemcpyAsync(m->d_spawn_groups, dev.data(), sizeof(SpawnGroupDev) * dev.size(), cudaMemcpyHostToDevice,
+                                m->stream));
+    spawn_groups_kernel<<<div_up(static_cast<uint32_t>(n), 256), 256, 0, m->stream>>>(
+        m->app, m->app_n, static_cast<uint32_t>(n), static_cast<const SpawnGroupDev*>(m->d_spawn_groups),
+        static_cast<uint32_t>(dev.size()), seed, counter);
+    m->launches += 1;
+    CUDA_TRY(m, cudaGetLastError());
+    m->app_n += static_cast<uint32_t>(n);
+    m->table_valid = false;
+    return PEDONI_OK;
 }
 
 int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const uint32_t* dest, const float* vel_xy,

@@ -121,6 +121,16 @@ class SocialForceModelCuda:
         assert pos.size == 2 * n and v0.size == n
         _capi.check(self._lib.pedoni_spawn(self._h, n, _fp(pos), _up(dest), _fp(v0)), self._h)
 
+    def spawn_groups(self, groups, seed: int, counter: int) -> int:
+        """Device-side spawn (pedoni_spawn_groups). groups: [(p1, p2, destination, count)]. Returns how many
+        stream numbers were consumed (3 per pedestrian)."""
+        arr = (_capi.PedoniSpawnGroup * len(groups))(*[
+            _capi.PedoniSpawnGroup(float(np.float32(p1[0])), float(np.float32(p1[1])), float(np.float32(p2[0])),
+                                   float(np.float32(p2[1])), int(d), int(c)) for p1, p2, d, c in groups])
+        _capi.check(self._lib.pedoni_spawn_groups(self._h, len(groups), arr, C.c_uint64(seed & (2 ** 64 - 1)),
+                                                  C.c_uint64(counter)), self._h)
+        return 3 * sum(int(g[3]) for g in groups)
+
     def rebuild(self) -> None:
         _capi.check(self._lib.pedoni_rebuild(self._h), self._h)
 
@@ -249,6 +259,9 @@ class SlabGroup:
     def spawn_arrays(self, pos, dest, v0) -> None:  # replicated list; each slab keeps the rows it owns
         for s in self.slabs:
             s.spawn_arrays(pos, dest, v0)
+
+    def spawn_groups(self, groups, seed: int, counter: int) -> int:
+        return [s.spawn_groups(groups, seed, counter) for s in self.slabs][0]
 
     def upload_state(self, pos, dest, vel, v0) -> None:
         for s in self.slabs:

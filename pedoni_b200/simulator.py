@@ -100,11 +100,15 @@ class Simulator:
     the tests' oracle adapter. It must offer spawn_arrays(pos, dest, v0) + rebuild() (the two halves of
     `spawn_pedestrians`), step() (`update_states`), get_pedestrian_count() and download()."""
 
-    def __init__(self, options, scenario, field, model, seed: int = 0x5EED0001, count_every: int = 1):
+    def __init__(self, options, scenario, field, model, seed: int = 0x5EED0001, count_every: int = 1,
+                 device_spawn: bool = False):
         self.options, self.scenario, self.field, self.model = options, scenario, field, model
         self.step = 0
         self.rng = SpawnStream(seed)
         self.spawned_total = 0
+        # draw positions and desired speeds on the device (pedoni_spawn_groups) instead of uploading them;
+        # same stream numbers either way, so the two modes give identical runs
+        self.device_spawn = bool(device_spawn) and hasattr(model, "spawn_groups")
         self.count_every = max(1, int(count_every))  # counting blocks; headless runs may sample it
         self._last_count = 0
         # lib.rs:37-52: "once" groups are spawned at construction
@@ -121,20 +125,25 @@ class Simulator:
         return pos, dest
 
     def _spawn(self, kind: str) -> int:
-        pos_l, dest_l = [], []
+        """Stream order per call: every group's count first (Poisson draws), then one uniform per pedestrian,
+        group after group, then the desired speeds (sfm.rs:54, in push order) — the same on the host path
+        and on the device path (pedoni_spawn_groups), so the two give bit-identical runs."""
+        groups = []
         for ped in self.scenario.pedestrians:
             if ped.spawn.kind != kind:
                 continue
             # lib.rs:74: poisson(frequency / 10.0) new pedestrians per 0.1 s tick
             count = ped.spawn.count if kind == "once" else self.rng.poisson(ped.spawn.frequency / 10.0)
             if count > 0:
-                p, d = self._draw_group(ped, count)
-                pos_l.append(p)
-                dest_l.append(d)
-        n = sum(len(d) for d in dest_l)
-        if n:
-            pos, dest = np.concatenate(pos_l), np.concatenate(dest_l)
-            v0 = self.rng.normal_approx(n, 1.34, 0.26)  # sfm.rs:54, drawn in push order
+                groups.append((ped, count))
+        n = sum(c for _, c in groups)
+        if n and self.device_spawn:
+            table = [(*self.scenario.waypoints[ped.origin].line, ped.destination, c) for ped, c in groups]
+            self.rng.k += self.model.spawn_groups(table, int(self.rng.seed), self.rng.k)
+        elif n:
+            drawn = [self._draw_group(ped, c) for ped, c in groups]
+            pos, dest = np.concatenate([d[0] for d in drawn]), np.concatenate([d[1] for d in drawn])
+            v0 = self.rng.normal_approx(n, 1.34, 0.26)
             self.model.spawn_arrays(pos, dest, v0)
         self.model.rebuild()  # spawn_pedestrians rebuilds the grid even with no newcomers (lib.rs:85, sfm.rs:58)
         self.spawned_total += n

@@ -158,3 +158,25 @@ spawn = { kind = "once", count = 40 }
     assert len(counts) == 400 and counts[0] >= 40 and max(counts) > 40   # the "once" group, then the inflow
     assert counts[-1] < max(counts)                                      # and people do arrive and leave
     assert log["preprocess_metrics"]["time_calc_field"] > 0
+
+
+@pytest.mark.parametrize("name", ["bottleneck", "evacuation", "random"])
+def test_device_side_spawn_equals_host_side_spawn(name):
+    """pedoni_spawn_groups draws positions and desired speeds on the device from the
+    same counter-based stream numbers the harness uses: the runs are bit-identical."""
+    from pedoni_b200 import SimulatorOptions, SocialForceModelCuda
+    from pedoni_b200.simulator import Simulator
+    sc = helpers.load_scenario(name)
+    opts = SimulatorOptions()
+    field = helpers.oracle_field(sc, opts.field_grid_unit)
+    sims = [Simulator(opts, sc, field, SocialForceModelCuda(opts, sc, field, math_mode=PEDONI_MATH_STRICT), seed=9,
+                      device_spawn=dev) for dev in (False, True)]
+    for t in range(120):
+        counts = [s.tick().active_ped_count for s in sims]
+        assert counts[0] == counts[1], f"tick {t}"
+    a, b = sims[0].model.download(), sims[1].model.download()
+    assert len(a[1]) > 0 and sims[0].rng.k == sims[1].rng.k
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
+    for s in sims:
+        s.model.close()
