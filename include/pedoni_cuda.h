@@ -177,6 +177,25 @@ int pedoni_download(PedoniModel* model, float* pos_xy, uint32_t* destination, fl
 int pedoni_download_begin(PedoniModel* model, float* pos_xy, uint32_t* destination, uint32_t cap);
 int pedoni_download_end(PedoniModel* model, uint32_t* n_out);
 
+/*
+ * Aggregate observables reduced ON THE DEVICE instead of downloading every
+ * pedestrian: population (total and by destination), mean speed, the lane histogram of a counter-flow
+ * corridor (mean x-velocity and population per y-bin over [y0, y1), at most 64 bins; n_bins = 0 skips
+ * it) and the cumulative number of pedestrians that reached their destination, by destination (removed by
+ * the predicate of sfm.rs:69 — not those that left the grid or turned NaN); its time derivative is the
+ * flow rate. Destinations >= 15 are lumped into entry 15. Slab handles report their own rows. Blocks.
+ */
+typedef struct PedoniObservables {
+    uint32_t count;
+    float mean_speed;
+    uint32_t per_destination[16];
+    uint64_t arrived[16];
+    uint32_t n_bins;
+    uint32_t bin_count[64];
+    float bin_mean_vx[64];
+} PedoniObservables;
+int pedoni_observe(PedoniModel* model, float y0, float y1, uint32_t n_bins, PedoniObservables* out);
+
 /* Replace the whole agent state (parity tests, checkpoint restore). Unsorted: call pedoni_rebuild. */
 int pedoni_upload_state(PedoniModel* model, uint32_t n, const float* pos_xy, const uint32_t* destination,
                         const float* vel_xy, const float* desired_speed);

@@ -59,6 +59,12 @@ class PedoniSpawnGroup(C.Structure):
                 ("destination", C.c_uint32), ("count", C.c_uint32)]
 
 
+class PedoniObservables(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("mean_speed", C.c_float), ("per_destination", C.c_uint32 * 16),
+                ("arrived", C.c_uint64 * 16), ("n_bins", C.c_uint32), ("bin_count", C.c_uint32 * 64),
+                ("bin_mean_vx", C.c_float * 64)]
+
+
 class PedoniKernelTimes(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("key_ms", "histogram_ms", "scan_ms", "scatter_ms", "gather_ms", "force_ms", "comm_ms")] + \
@@ -82,6 +88,7 @@ SIGNATURES = {
     "pedoni_download": (C.c_int, [C.c_void_p, c_float_p, c_u32_p, c_float_p, c_float_p, C.c_uint32, c_u32_p]),
     "pedoni_download_begin": (C.c_int, [C.c_void_p, c_float_p, c_u32_p, C.c_uint32]),
     "pedoni_download_end": (C.c_int, [C.c_void_p, c_u32_p]),
+    "pedoni_observe": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_uint32, C.POINTER(PedoniObservables)]),
     "pedoni_upload_state": (C.c_int, [C.c_void_p, C.c_uint32, c_float_p, c_u32_p, c_float_p, c_float_p]),
     "pedoni_grid_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pedoni_cell_table": (C.c_int, [C.c_void_p, c_u32_p, C.c_uint32, c_u32_p]),

@@ -88,6 +88,7 @@ struct ForceParams {
     uint32_t* cell_count;        // per-cell population of the NEXT rebuild (zeroed by the previous one)
     uint32_t* error_flag;
     unsigned long long* updates_total;  // += owned agents of this launch (thread 0 of block 0)
+    unsigned long long* arrived;        // [16] cumulative arrivals by destination (owned agents only)
     const float* obstacle_edges;  // segment-wall variant only
     int n_obstacles;
 };
@@ -508,7 +509,10 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     p.out.vel[id] = vn;
     p.out.v0[id] = v0;
     p.out.dest[id] = dest;
-    count_key(sort_key(p.grid, p.field, pn, dest, p.error_flag), p.cell_count, p.keys_out + id, p.ticket_out + id);
+    // ghost-row agents are integrated twice (here and by their owner): only the owner counts an arrival
+    const bool owned = id >= p.d_owned[0] && id < p.d_owned[1];
+    count_key(sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned), p.cell_count, p.keys_out + id,
+              p.ticket_out + id);
     // Slab handles exchange two ghost rows per tick, which covers every move of less than one grid row
     // (1.4 m per 0.1 s); anything faster would silently vanish at a slab boundary, so flag it.
     if (p.grid.slab) {

@@ -154,15 +154,19 @@ __device__ __forceinline__ void count_key(uint32_t key, uint32_t* __restrict__ c
 // ---- key: only for logical indices in [t_begin, t_end) whose keys are not fresh -------------------
 __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin, uint32_t t_end, GridView g,
                                                   FieldView f, uint32_t* __restrict__ cell_count,
-                                                  uint32_t* __restrict__ error_flag) {
+                                                  uint32_t* __restrict__ error_flag,
+                                                  unsigned long long* __restrict__ arrived) {
     uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
     const Located l = locate(in, t);
     if (!l.live) return;
     // Spawn lists are replicated to every slab and ghost rows are copies: sort_key keeps an agent only
     // on the handle that owns its row.
-    count_key(sort_key(g, f, l.a.pos[l.idx], l.a.dest[l.idx], error_flag), cell_count, l.keys + l.idx,
-              l.ticket + l.idx);
+    // a replicated spawn that stands on its destination is counted as arrived by the slab owning its row
+    const float2 pos = l.a.pos[l.idx];
+    const int row = __float2int_rz(S::div(pos.y, g.unit));
+    count_key(sort_key(g, f, pos, l.a.dest[l.idx], error_flag, arrived, row >= g.own_row0 && row < g.own_row1),
+              cell_count, l.keys + l.idx, l.ticket + l.idx);
 }
 
 // ---- scan: exclusive prefix over n_cells counters in ONE pass (chained scan with decoupled look-back) --
@@ -518,6 +522,67 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(AgentArrays a, uint32_
         a.vel[base + i] = __ldcg(msg.vel(nx, halo_cap) + i);
         a.v0[base + i] = __ldcg(msg.v0(nx, halo_cap) + i);
         a.dest[base + i] = __ldcg(msg.dest(nx, halo_cap) + i);
+    }
+}
+
+// ---- observables: one pass over the owned pedestrians -----------------------
+struct ObserveOut {  // device mirror of PedoniObservables' reduced fields
+    unsigned int count;
+    float speed_sum;
+    unsigned int per_destination[16];
+    float bin_vx_sum[64];
+    unsigned int bin_count[64];
+};
+
+__global__ void __launch_bounds__(256) observe_kernel(AgentArrays a, const uint32_t* __restrict__ owned, uint32_t upper,
+                                                      float y0, float inv_bin, uint32_t n_bins,
+                                                      ObserveOut* __restrict__ out) {
+    __shared__ unsigned int s_dest[16];
+    __shared__ float s_vx[64];
+    __shared__ unsigned int s_cnt[64];
+    __shared__ float s_speed[8];
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        s_vx[k] = 0.0f;
+        s_cnt[k] = 0u;
+        if (k < 16) s_dest[k] = 0u;
+    }
+    __syncthreads();
+    const uint32_t begin = owned[0], end = owned[1];
+    float speed = 0.0f;
+    unsigned int mine = 0;
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end && i - begin < upper;
+         i += gridDim.x * blockDim.x) {
+        const float2 v = a.vel[i], p = a.pos[i];
+        speed += sqrtf(v.x * v.x + v.y * v.y);
+        mine += 1;
+        atomicAdd(s_dest + min(a.dest[i], 15u), 1u);
+        const float b = (p.y - y0) * inv_bin;
+        if (n_bins > 0 && b >= 0.0f && b < static_cast<float>(n_bins)) {
+            atomicAdd(s_vx + static_cast<int>(b), v.x);
+            atomicAdd(s_cnt + static_cast<int>(b), 1u);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        speed += __shfl_down_sync(0xFFFFFFFFu, speed, d);
+        mine += __shfl_down_sync(0xFFFFFFFFu, mine, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_speed[threadIdx.x >> 5] = speed;
+        atomicAdd(&out->count, mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += s_speed[w];
+        atomicAdd(&out->speed_sum, t);
+    }
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        if (k < 16 && s_dest[k]) atomicAdd(out->per_destination + k, s_dest[k]);
+        if (s_cnt[k]) {
+            atomicAdd(out->bin_vx_sum + k, s_vx[k]);
+            atomicAdd(out->bin_count + k, s_cnt[k]);
+        }
     }
 }
 

@@ -110,6 +110,8 @@ struct PedoniModel {
     int rcur = 0;
     uint32_t* d_error = nullptr;
     unsigned long long* d_updates = nullptr;
+    unsigned long long* d_arrived = nullptr;  // [16] cumulative arrivals by destination
+    ObserveOut* d_observe = nullptr;
     uint64_t launches = 0;  // kernels launched by this handle
 
     // pinned, mapped: [0] = tick << 32 | n_owned (published after every rebuild)
@@ -414,6 +416,7 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     p.cell_count = m->d_cell_count;
     p.error_flag = m->d_error;
     p.updates_total = m->d_updates;
+    p.arrived = m->d_arrived;
     p.obstacle_edges = m->d_edges;
     p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
     const size_t smem = kForceSmemBytes;  // tile + neighbour lists; the segment-wall variant reuses the tile
@@ -750,6 +753,9 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     CREATE_TRY(cudaMalloc(&m->d_error, sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&m->d_updates, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(m->d_updates, 0, sizeof(unsigned long long), m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_arrived, 16 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemsetAsync(m->d_arrived, 0, 16 * sizeof(unsigned long long), m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_observe, sizeof(ObserveOut)));
     CREATE_TRY(cudaMemsetAsync(m->d_cell_start, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
     CREATE_TRY(cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
@@ -790,7 +796,7 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_perm,
                     (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_status, (void*)m->d_tile_ticket,
                     (void*)m->d_ranges,
-                    (void*)m->d_error, (void*)m->d_updates, (void*)m->d_distance, (void*)m->d_potential,
+                    (void*)m->d_error, (void*)m->d_updates, (void*)m->d_arrived, (void*)m->d_observe, (void*)m->d_distance, (void*)m->d_potential,
                     (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena, m->d_spawn_groups})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
@@ -927,7 +933,7 @@ static int rebuild_impl(PedoniModel* m) {
         if (t_begin < total) {
             ScopedTimer t(m, kKey, s);
             key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field,
-                                                                   m->d_cell_count, m->d_error);
+                                                                   m->d_cell_count, m->d_error, m->d_arrived);
             m->launches += 1;
         }
     }
@@ -1223,6 +1229,40 @@ int pedoni_download_end(PedoniModel* m, uint32_t* n_out) {
     const uint32_t n = m->h_snap_range[1] - m->h_snap_range[0];
     if (n_out) *n_out = n;
     if (n > m->dl_cap) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", m->dl_cap, n);
+    return PEDONI_OK;
+}
+
+int pedoni_observe(PedoniModel* m, float y0, float y1, uint32_t n_bins, PedoniObservables* out) {
+    if (!m || !out || n_bins > 64 || (n_bins > 0 && !(y1 > y0))) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    int rc = sync_all(m);
+    if (rc != PEDONI_OK) return rc;
+    rc = check_device_error(m);
+    if (rc != PEDONI_OK) return rc;
+    std::memset(out, 0, sizeof *out);
+    out->n_bins = n_bins;
+    CUDA_TRY(m, cudaMemsetAsync(m->d_observe, 0, sizeof(ObserveOut), m->stream));
+    const uint32_t upper = std::max<uint32_t>(m->owned_upper, 1);
+    const uint32_t blocks = std::min<uint32_t>(div_up(upper, 256), 148 * 8);
+    observe_kernel<<<blocks, 256, 0, m->stream>>>(m->buf[m->cur], m->range(kRangeOwned), upper, y0,
+                                                  n_bins ? static_cast<float>(n_bins) / (y1 - y0) : 0.0f, n_bins,
+                                                  m->d_observe);
+    m->launches += 1;
+    ObserveOut h{};
+    unsigned long long arrived[16];
+    CUDA_TRY(m, cudaMemcpyAsync(&h, m->d_observe, sizeof h, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(m, cudaMemcpyAsync(arrived, m->d_arrived, sizeof arrived, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    out->count = h.count;
+    out->mean_speed = h.count ? h.speed_sum / static_cast<float>(h.count) : 0.0f;
+    for (int k = 0; k < 16; ++k) {
+        out->per_destination[k] = h.per_destination[k];
+        out->arrived[k] = arrived[k];
+    }
+    for (uint32_t k = 0; k < n_bins; ++k) {
+        out->bin_count[k] = h.bin_count[k];
+        out->bin_mean_vx[k] = h.bin_count[k] ? h.bin_vx_sum[k] / static_cast<float>(h.bin_count[k]) : 0.0f;
+    }
     return PEDONI_OK;
 }
 

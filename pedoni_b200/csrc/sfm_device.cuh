@@ -235,15 +235,23 @@ __device__ __forceinline__ int2 cell_of(float2 pos, float unit) {
 //    agent and raises the device error flag.
 //  - slab handles: an agent whose row belongs to another slab is dropped HERE; the owner of that row
 //    integrates the same agent redundantly (it holds it as a ghost) and adopts it in its own rebuild.
+//  - `arrived` (16 cumulative counters by destination, the last one lumps destinations >= 15): a
+//    pedestrian removed BY THE PREDICATE (it reached its destination) is counted once, by the handle in
+//    whose rows `count_arrival` says it belongs — the observable "flow" (SURVEY.md section 8, row f3).
 __device__ __forceinline__ uint32_t sort_key(const GridView& g, const FieldView& f, float2 pos, uint32_t dest,
-                                             uint32_t* error_flag) {
+                                             uint32_t* error_flag, unsigned long long* arrived = nullptr,
+                                             bool count_arrival = false) {
     int2 c = cell_of(pos, g.unit);
     if (c.x < 0 || c.y < 0 || c.x >= g.nx || c.y >= g.ny) return kKeyDrop;
     if (dest >= static_cast<uint32_t>(f.n_maps)) {
         atomicOr(error_flag, kErrBadDestination);
         return kKeyDrop;
     }
-    if (!(get_potential(f, dest, pos) > 0.25f)) return kKeyDrop;
+    const float potential = get_potential(f, dest, pos);
+    if (!(potential > 0.25f)) {
+        if (count_arrival && potential == potential) atomicAdd(arrived + min(dest, 15u), 1ull);
+        return kKeyDrop;
+    }
     if (c.y < g.own_row0 || c.y >= g.own_row1) return kKeyDrop;
     return static_cast<uint32_t>(c.y - g.row_base) * static_cast<uint32_t>(g.nx) + static_cast<uint32_t>(c.x);
 }

@@ -171,6 +171,17 @@ class SocialForceModelCuda:
         pos, dest = self._dl
         return pos[: n.value], dest[: n.value]
 
+    def observe(self, y_range=(0.0, 1.0), bins: int = 0) -> dict:
+        """Device-side observables (pedoni_observe): no pedestrian leaves the GPU."""
+        o = _capi.PedoniObservables()
+        _capi.check(self._lib.pedoni_observe(self._h, float(y_range[0]), float(y_range[1]), int(bins), C.byref(o)),
+                    self._h)
+        return {"count": o.count, "mean_speed": o.mean_speed,
+                "per_destination": np.array(o.per_destination[:], np.uint32),
+                "arrived": np.array(o.arrived[:], np.uint64),
+                "bin_count": np.array(o.bin_count[:bins], np.uint32),
+                "bin_mean_vx": np.array(o.bin_mean_vx[:bins], np.float32)}
+
     def grid_shape(self):
         ny, nx = C.c_int32(), C.c_int32()
         _capi.check(self._lib.pedoni_grid_shape(self._h, C.byref(ny), C.byref(nx)), self._h)

@@ -53,6 +53,15 @@ def lane_count(pos, vel, y_range, bins: int = 32, min_agents: int = 2) -> int:
     return int((signs[1:] != signs[:-1]).sum()) + 1
 
 
+def lane_count_from_bins(bin_mean_vx, bin_count, min_agents: int = 2) -> int:
+    """`lane_count` on the histogram pedoni_observe reduces on the device."""
+    signs = [np.sign(v) for v, c in zip(bin_mean_vx, bin_count) if c >= min_agents and v != 0]
+    if not signs:
+        return 0
+    signs = np.asarray(signs)
+    return int((signs[1:] != signs[:-1]).sum()) + 1
+
+
 def mean_speed(vel) -> float:
     vel = np.asarray(vel)
     return float(np.linalg.norm(vel, axis=1).mean()) if len(vel) else 0.0

@@ -35,13 +35,17 @@ def test_config_struct_layout_matches_the_header(tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pedoni_cuda.h"\nint main(void){\n'
                    'printf("%zu\\n", sizeof(PedoniConfig));\n' +
                    "".join(f'printf("%zu\\n", offsetof(PedoniConfig, {f}));\n' for f in fields) +
-                   'printf("%zu\\n", sizeof(PedoniKernelTimes));\nreturn 0;}\n')
+                   'printf("%zu\\n", sizeof(PedoniKernelTimes));\n'
+                   'printf("%zu\\n", sizeof(PedoniObservables));\nprintf("%zu\\n", sizeof(PedoniSpawnGroup));\n'
+                   'printf("%zu\\n", offsetof(PedoniObservables, arrived));\nreturn 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(HEADER.parent), str(src), "-o", str(exe)], check=True)
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert out[0] == C.sizeof(_capi.PedoniConfig)
-    assert out[1:-1] == [getattr(_capi.PedoniConfig, f).offset for f in fields]
-    assert out[-1] == C.sizeof(_capi.PedoniKernelTimes)
+    assert out[1:-4] == [getattr(_capi.PedoniConfig, f).offset for f in fields]
+    assert out[-4] == C.sizeof(_capi.PedoniKernelTimes)
+    assert out[-3] == C.sizeof(_capi.PedoniObservables) and out[-2] == C.sizeof(_capi.PedoniSpawnGroup)
+    assert out[-1] == _capi.PedoniObservables.arrived.offset
 
 
 def test_slab_rows_is_host_only():

@@ -180,3 +180,34 @@ def test_device_side_spawn_equals_host_side_spawn(name):
         np.testing.assert_array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
     for s in sims:
         s.model.close()
+
+
+def test_device_side_observables_match_downloaded_state():
+    """pedoni_observe (SURVEY section 8 row f3) against numpy on the downloaded pedestrians, on lanes.toml;
+    the cumulative arrival counters against the bookkeeping spawned - active."""
+    from pedoni_b200 import SimulatorOptions, SocialForceModelCuda
+    from pedoni_b200.simulator import Simulator
+    sc = helpers.load_scenario("lanes")
+    opts = SimulatorOptions()
+    field = helpers.oracle_field(sc, opts.field_grid_unit)
+    sim = Simulator(opts, sc, field, SocialForceModelCuda(opts, sc, field, math_mode=PEDONI_MATH_FAST), seed=12,
+                    count_every=10 ** 9, device_spawn=True)
+    for _ in range(1200):
+        sim.tick()
+    sim.model.rebuild()  # settle this tick's arrivals so that count == what download returns
+    o = sim.model.observe((0.0, 8.0), bins=8)
+    pos, dest, vel, _ = sim.model.download()
+    assert o["count"] == len(dest) > 20
+    np.testing.assert_array_equal(o["per_destination"][:2], np.bincount(dest, minlength=2)[:2])
+    assert abs(o["mean_speed"] - observables.mean_speed(vel)) < 1e-4
+    idx = np.clip((pos[:, 1] / 1.0).astype(int), 0, 7)
+    for b in range(8):
+        assert o["bin_count"][b] == (idx == b).sum()
+        if (idx == b).any():
+            assert abs(o["bin_mean_vx"][b] - vel[idx == b, 0].mean()) < 1e-4
+    lanes_dev = observables.lane_count_from_bins(o["bin_mean_vx"], o["bin_count"], 1)
+    assert lanes_dev == observables.lane_count(pos, vel, (0.0, 8.0), bins=8, min_agents=1)
+    # everybody who is gone arrived (nobody leaves the grid or turns NaN in this corridor)
+    assert int(o["arrived"].sum()) == sim.spawned_total - len(dest) > 50
+    assert o["arrived"][0] > 0 and o["arrived"][1] > 0
+    sim.model.close()
