@@ -361,7 +361,7 @@ def run_ours(args):
             "kernel_ms_per_step": step_kernel_ms,
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU leg is measured once, at N = 1
             out["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(out))
     model.close()
