@@ -134,8 +134,13 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (ts + tc) / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic uniform crowd, 10M pedestrians, open domain (bounded CPU sample)",
-                   "density_per_m2": args.density, "sample_agents": args.cpu_agents},
+        # the same workload as the CUDA arm; each timed step is a tick of a bounded sample of it
+        "config": {"workload": f"synthetic uniform crowd, {args.agents} pedestrians, open domain "
+                               f"{SyntheticCrowd(n=args.agents, density=args.density).side:.0f} m x "
+                               f"{SyntheticCrowd(n=args.agents, density=args.density).side:.0f} m (BASELINE.json configs[4])",
+                   "density_per_m2": args.density, "neighbor_unit_m": 1.4, "field_unit_m": 0.25,
+                   "sample_agents": args.cpu_agents,
+                   "implementation": "C++ restatement of the Rust reference (oracle/): the Rust toolchain is absent"},
         "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample,
                          "time_spawn_s": ts, "time_calc_state_s": tc, "wall_s": wall},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
