@@ -938,25 +938,34 @@ static int rebuild_impl(PedoniModel* m) {
         }
     }
     advance_tick(m, (uint64_t)m->app_n + (uint64_t)m->n_sides() * m->halo_cap);
-    {
-        ScopedTimer t(m, kScan, s);
-        ScanLayout layout{m->own_begin_cell, m->own_end_cell, static_cast<uint32_t>(m->grid.nx), m->has_below,
-                          m->has_above,     m->ranges(m->rcur ^ 1), m->h_pub_dev,               m->tick};
-        scan_cells_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->array_offset,
-                                                              m->d_cell_start, m->d_tile_status, m->d_tile_ticket,
-                                                              m->n_tiles, layout);
+    ScanLayout layout{m->own_begin_cell, m->own_end_cell, static_cast<uint32_t>(m->grid.nx), m->has_below,
+                      m->has_above,     m->ranges(m->rcur ^ 1), m->h_pub_dev,               m->tick};
+    if (total <= kSmallRebuildMaxAgents && m->n_cells <= kSmallRebuildMaxCells) {
+        // small crowd: scan + scatter + gather in one CTA, one launch
+        ScopedTimer t(m, kGather, s);
+        rebuild_small_kernel<<<1, 1024, 0, s>>>(in, total, m->d_cell_count, m->n_cells, m->array_offset, m->d_cell_start,
+                                                m->d_perm, m->buf[m->cur ^ 1], layout);
         m->launches += 1;
-    }
-    if (total > 0) {
+    } else {
         {
-            ScopedTimer t(m, kScatter, s);
-            scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm);
+            ScopedTimer t(m, kScan, s);
+            scan_cells_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->array_offset,
+                                                                  m->d_cell_start, m->d_tile_status, m->d_tile_ticket,
+                                                                  m->n_tiles, layout);
             m->launches += 1;
         }
-        {
-            ScopedTimer t(m, kGather, s);
-            gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm, m->buf[m->cur ^ 1]);
-            m->launches += 1;
+        if (total > 0) {
+            {
+                ScopedTimer t(m, kScatter, s);
+                scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm);
+                m->launches += 1;
+            }
+            {
+                ScopedTimer t(m, kGather, s);
+                gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm,
+                                                                m->buf[m->cur ^ 1]);
+                m->launches += 1;
+            }
         }
     }
     m->cur ^= 1;
