@@ -16,11 +16,52 @@ import pedoni_b200 as pb  # noqa: E402
 from pedoni_b200.synthetic import SyntheticCrowd  # noqa: E402
 
 
+def scenario_mode(rank, world, local, name, ticks):
+    """A shipped scenario through the Simulator facade on every rank (same seed: the spawn lists are
+    replicated, each slab keeps its rows): growing, very unevenly distributed crowd."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import helpers
+    from pedoni_b200.simulator import Simulator
+    sc = helpers.load_scenario(name)
+    opts = pb.SimulatorOptions()
+    field = pb.Field.from_scenario(sc, opts.field_grid_unit)
+    slab = pb.SocialForceModelCuda(opts, sc, field, device=local, math_mode=pb.PEDONI_MATH_FAST, slab_rank=rank,
+                                   slab_count=world, halo_capacity=8192)
+    uid = [pb.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    slab.comm_init(uid[0])
+    sim = Simulator(opts, sc, field, slab, seed=4, count_every=10 ** 9, device_spawn=True)
+    for _ in range(ticks):
+        sim.tick()
+    part = slab.download()
+    parts = [None] * world
+    dist.gather_object(part, parts if rank == 0 else None, dst=0)
+    ok = True
+    if rank == 0:
+        whole = Simulator(opts, sc, field, pb.SocialForceModelCuda(opts, sc, field, device=local,
+                                                                   math_mode=pb.PEDONI_MATH_FAST),
+                          seed=4, count_every=10 ** 9, device_spawn=True)
+        for _ in range(ticks):
+            whole.tick()
+        want = whole.model.download()
+        u32 = lambda a: np.ascontiguousarray(a).view(np.uint32)  # noqa: E731
+        got = [np.concatenate([p[k] for p in parts]) for k in range(4)]
+        ok = all(g.shape == w.shape and (u32(g) == u32(w)).all() for g, w in zip(got, want))
+        print(f"NCCL-SLABS {'OK' if ok else 'MISMATCH'} scenario={name} world={world} n={len(want[1])} "
+              f"transport={slab.slab_transport()!r} owned={[len(p[1]) for p in parts]}", flush=True)
+    slab.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    n_agents, ticks = int(sys.argv[1]), int(sys.argv[2])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")  # plumbing only: the data path is the library's own NCCL communicator
+    if sys.argv[1].startswith("scenario:"):
+        return scenario_mode(rank, world, local, sys.argv[1].split(":", 1)[1], int(sys.argv[2]))
+    n_agents, ticks = int(sys.argv[1]), int(sys.argv[2])
     crowd = SyntheticCrowd(n=n_agents)
     sc, field = crowd.scenario(), crowd.field()
     pos, dest, vel, v0 = crowd.agents()

@@ -33,3 +33,15 @@ def test_multi_gpu_slabs_equal_whole_domain(world, transport):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "NCCL-SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     assert ("peer-memory" if transport == "peer" else "nccl send/recv") in r.stdout, r.stdout[-500:]
+
+
+def test_multi_gpu_slabs_on_a_growing_scenario():
+    """bottleneck.toml for 400 ticks on 2 GPUs (peer-memory transport, device-side spawning, buffers growing,
+    nearly everybody in the slab that holds the gap) = whole domain, bit for bit."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29640",
+           str(ROOT / "tests" / "nccl_slab_worker.py"), "scenario:bottleneck", "400"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "NCCL-SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
