@@ -6,7 +6,7 @@ Python, written from the Rust sources (not from oracle/*.cpp):
 
 Its only purpose is to cross-check the C++ oracle (tests/test_oracle_cross_check.py): the reference holds
 no test for the step and cannot be compiled here, so two restatements written separately agreeing bit for
-bit (cell table, order, despawns) and to the last ulp of exp (numpy's float32 exp is not glibc's) is the
+bit (cell table, order, despawns) and, for positions and velocities, up to the last bit of exp, is the
 strongest pin available. Every arithmetic operation is a numpy float32 scalar operation, i.e. one IEEE
 rounding per operation and no FMA, like rustc's f32 code. Pure-Python loops: small cases only.
 """
@@ -19,6 +19,18 @@ import numpy as np
 f32 = np.float32
 FMAX = f32(1e12)          # util.rs:45
 COS_PHI = f32(-0.17364817766693036)   # sfm.rs:16
+
+
+def _exp(x):
+    """f32::exp: a correctly rounded stand-in (fp64 exp rounded once). glibc's expf, which the Rust code and
+    the C++ oracle call, is a 0.502-ulp routine: the two differ in the last bit about once in 10^3 calls."""
+    x = float(x)
+    if math.isnan(x):
+        return f32(np.nan)
+    try:
+        return f32(math.exp(x))
+    except OverflowError:
+        return f32(np.inf)
 
 
 def _as_i32(v) -> int:
@@ -143,7 +155,7 @@ class PyModel:
             sx, sy = f32(dirx + f32(t1x / t1len)), f32(diry + f32(t1y / t1len))
             fb = f32(f32(4.0) * bb)
             nbx, nby = f32(f32(t2 * sx) / fb), f32(f32(t2 * sy) / fb)
-            coef = f32(f32(f32(2.1) / f32(0.3)) * f32(np.exp(f32(f32(-bb) / f32(0.3)))))
+            coef = f32(f32(f32(2.1) / f32(0.3)) * _exp(f32(f32(-bb) / f32(0.3))))
             fx, fy = f32(coef * nbx), f32(coef * nby)
             lhs = f32(f32(e[0] * f32(-fx)) + f32(e[1] * f32(-fy)))
             flen = f32(np.sqrt(f32(f32(fx * fx) + f32(fy * fy))))
@@ -178,7 +190,7 @@ class PyModel:
                     d = bilinear(self.dist, qx, qy)
                     dgx, dgy = sobel_filter(self.dist, qx, qy)
                     nx_, ny_ = _normalize(dgx, dgy)
-                    coef = f32(f32(f32(10.0) * f32(0.2)) * f32(np.exp(f32(f32(-d) / f32(0.2)))))
+                    coef = f32(f32(f32(10.0) * f32(0.2)) * _exp(f32(f32(-d) / f32(0.2))))
                     ax, ay = f32(ax + f32(coef * f32(-nx_))), f32(ay + f32(coef * f32(-ny_)))
                 else:                                           # sfm.rs:193-237
                     for (ox0, oy0, ox1, oy1, w) in self.obstacles:
@@ -203,7 +215,7 @@ class PyModel:
                             if dists[k] > dists[kk]:
                                 k = kk
                         ux, uy = _normalize(*diffs[k])
-                        coef = f32(f32(f32(10.0) * f32(0.2)) * f32(np.exp(f32(f32(-dists[k]) / f32(0.2)))))
+                        coef = f32(f32(f32(10.0) * f32(0.2)) * _exp(f32(f32(-dists[k]) / f32(0.2))))
                         ax, ay = f32(ax + f32(coef * ux)), f32(ay + f32(coef * uy))
             acc.append((ax, ay))
         for a, (ax, ay) in zip(self.p, acc):                    # sfm.rs:243-254

@@ -1,7 +1,7 @@
 """CPU: the C++ oracle against a second restatement of the reference's step written independently in scalar
 numpy-float32 Python (tests/py_restatement.py). Integer outputs — populations, `neighbor_grid_indices`,
-order, destinations — must be identical; positions and velocities agree to the last bits of exp (numpy's
-float32 exp is not glibc's expf)."""
+order, destinations — must be identical; positions and velocities are bit-identical too, except where
+glibc's expf (0.502 ulp) and a correctly rounded exp disagree in the last bit (about one call in 10^3)."""
 import numpy as np
 import pytest
 
@@ -46,8 +46,13 @@ def test_step_agrees_with_the_cpp_oracle(use_distance_map):
         assert len(pd) == len(cd) and 100 < len(cd) < 160
         np.testing.assert_array_equal(pd, cd)
         np.testing.assert_array_equal(helpers.bits(p0), helpers.bits(c0))
+        np.testing.assert_array_equal(np.isnan(pp), np.isnan(cp))
         np.testing.assert_allclose(pp, cp, rtol=0, atol=2e-6)
         np.testing.assert_allclose(pv, cv, rtol=0, atol=2e-5)
+        # exp is the only operation not bit-identical by construction (correctly rounded here, glibc's 0.502-ulp
+        # expf in the oracle): the overwhelming majority of the output floats must be identical in every bit
+        differ = int((helpers.bits(pp) != helpers.bits(cp)).sum() + (helpers.bits(pv) != helpers.bits(cv)).sum())
+        assert differ <= 0.03 * (tick + 1) * (pp.size + pv.size), (tick, differ, pp.size + pv.size)
         if tick == 0:  # nothing but the sort has run: bit for bit
             np.testing.assert_array_equal(helpers.bits(pp), helpers.bits(cp))
         py.update_states()
