@@ -211,3 +211,30 @@ def test_device_side_observables_match_downloaded_state():
     assert int(o["arrived"].sum()) == sim.spawned_total - len(dest) > 50
     assert o["arrived"][0] > 0 and o["arrived"][1] > 0
     sim.model.close()
+
+
+@pytest.mark.parametrize("name,ticks", [("default", 900), ("random", 500), ("straight", 600), ("sparse", 300),
+                                        ("narrow-gap2", 250), ("bottleneck1", 400)])
+def test_population_and_speed_match_on_the_remaining_scenarios(name, ticks):
+    """The shipped scenarios without a named observable: population and mean speed at a fixed time and the
+    cumulative number of arrivals, fast math vs the oracle, 4 seeds each (means within 2 standard errors +
+    resolution; arrivals on the device come from pedoni_observe's counters)."""
+    pop, spd, arr = ([], []), ([], []), ([], [])
+    for seed in range(4):
+        cu, orc = helpers.simulator_pair(name, seed=400 + seed, math_mode=PEDONI_MATH_FAST)
+        cu.count_every = orc.count_every = 10 ** 9
+        for k, sim in enumerate((cu, orc)):
+            for _ in range(ticks):
+                sim.tick()
+            sim.model.rebuild()
+            p, d, v, _ = sim.model.download()
+            pop[k].append(len(d))
+            spd[k].append(observables.mean_speed(v[np.isfinite(v).all(1)]))
+            arr[k].append(sim.spawned_total - len(d))
+        arrived_dev = int(cu.model.observe()["arrived"].sum())
+        assert arrived_dev <= arr[0][-1]  # the rest left the grid or turned NaN
+        cu.model.close()
+    assert max(pop[1]) > 0
+    print(name, "population cuda/oracle:", _agree(pop[0], pop[1], 2.0 + 0.01 * np.mean(pop[1]), f"{name} population"))
+    print(name, "mean speed cuda/oracle:", _agree(spd[0], spd[1], 0.03, f"{name} mean speed"))
+    print(name, "gone cuda/oracle:", _agree(arr[0], arr[1], 2.0 + 0.01 * np.mean(pop[1]), f"{name} pedestrians gone"))
