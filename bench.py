@@ -213,6 +213,7 @@ def run_ours(args):
     for lo in range(0, args.agents, chunk):
         pos, dest, vel, v0 = crowd.agents(lo, min(lo + chunk, args.agents))
         model.spawn_arrays(pos, dest, v0)
+    barrier()  # ranks generate the crowd at different speeds; the first ghost exchange should find everybody there
     model.rebuild()
     n0 = model.get_pedestrian_count()
     for _ in range(args.relax):

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(AgentArrays a, const uin
 // Also completes the cell table for the ghost rows and the compute / edge ranges.
 // wait_seq != 0 (peer-memory transport): the strip is written by the neighbour's pack kernel; poll the
 // local arrival flag until it reaches this exchange's ordinal (the neighbour may already be one ahead —
-// it writes alternate slots), bounded by a time-out so that a dead peer cannot hang the GPU.
+// it writes alternate slots), bounded by a 20 s time-out so that a dead peer cannot hang the GPU for good.
 __global__ void __launch_bounds__(256) halo_unpack_kernel(AgentArrays a, uint32_t* __restrict__ cell_start,
                                                           uint32_t own_begin_cell, uint32_t own_end_cell, uint32_t nx,
                                                           uint32_t halo_cap, uint32_t array_cap, HaloMessage below,
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(AgentArrays a, uint32_
             const unsigned long long t0 = global_timer_ns();
             int timed_out = 0;
             while (static_cast<int32_t>(*flag - wait_seq) < 0) {
-                if (global_timer_ns() - t0 > 5000000000ull) {  // 5 s
+                if (global_timer_ns() - t0 > 20000000000ull) {  // 20 s
                     timed_out = 1;
                     break;
                 }

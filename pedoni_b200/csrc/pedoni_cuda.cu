@@ -451,7 +451,7 @@ int check_device_error(PedoniModel* m) {
                     "overran the arrays); raise PedoniConfig.halo_capacity", m->halo_cap);
     if (bits & kErrHaloTimeout)
         return fail(m, PEDONI_ERR_COMM,
-                    "slab %d of %d waited 5 s for a neighbour's ghost strip (peer-memory transport): a rank died or "
+                    "slab %d of %d waited 20 s for a neighbour's ghost strip (peer-memory transport): a rank died or "
                     "the ranks do not call pedoni_rebuild in lockstep", m->slab_rank, m->slab_count);
     return fail(m, PEDONI_ERR_STATE,
                 "a pedestrian crossed two or more neighbor-grid rows in one step; the slab decomposition "

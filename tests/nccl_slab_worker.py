@@ -74,6 +74,7 @@ def main():
     slab.comm_init(uid[0])
     transport = slab.slab_transport()
     slab.upload_state(pos, dest, vel, v0)
+    dist.barrier()
     slab.rebuild()
     n0 = slab.get_pedestrian_count()
     for _ in range(ticks):
