@@ -297,6 +297,19 @@ class SlabGroup:
         cat = lambda k: None if parts[0][k] is None else np.concatenate([p[k] for p in parts])  # noqa: E731
         return cat(0), cat(1), cat(2), cat(3)
 
+    def observe(self, y_range=(0.0, 1.0), bins: int = 0) -> dict:
+        """Device-side observables of every slab, combined (counts add; means are population-weighted)."""
+        parts = [s.observe(y_range, bins) for s in self.slabs]
+        count = sum(p["count"] for p in parts)
+        bin_count = sum(p["bin_count"].astype(np.int64) for p in parts)
+        vx_sum = sum(p["bin_mean_vx"].astype(np.float64) * p["bin_count"] for p in parts)
+        return {"count": count,
+                "mean_speed": float(sum(p["mean_speed"] * p["count"] for p in parts) / max(count, 1)),
+                "per_destination": sum(p["per_destination"].astype(np.int64) for p in parts),
+                "arrived": sum(p["arrived"].astype(np.int64) for p in parts),
+                "bin_count": bin_count,
+                "bin_mean_vx": np.where(bin_count > 0, vx_sum / np.maximum(bin_count, 1), 0.0).astype(np.float32)}
+
     def cell_table(self) -> np.ndarray:
         """Whole-domain `neighbor_grid_indices` stitched from the slabs' owned rows."""
         out, base = [np.zeros(1, np.uint32)], 0

@@ -158,6 +158,13 @@ def test_slabs_on_a_growing_non_uniform_crowd():
         if (t + 1) % 50 == 0:
             assert mw.active_ped_count == ms.active_ped_count > 0
     _assert_same(whole.model, slabs.model)
+    # device-side observables: the slabs' reductions add up to the whole domain's (arrivals are counted by
+    # the owner only, although ghost-row pedestrians are integrated twice)
+    ow, os_ = whole.model.observe((0.0, 200.0), 16), slabs.model.observe((0.0, 200.0), 16)
+    assert ow["count"] == os_["count"] and abs(ow["mean_speed"] - os_["mean_speed"]) < 1e-4
+    np.testing.assert_array_equal(ow["per_destination"], os_["per_destination"])
+    np.testing.assert_array_equal(ow["arrived"], os_["arrived"])
+    np.testing.assert_array_equal(ow["bin_count"], os_["bin_count"])
     per_slab = [s.get_pedestrian_count() for s in slabs.model.slabs]
     assert max(per_slab) > 0 and sum(per_slab) == whole.model.get_pedestrian_count() > 6000
     whole.model.close()
