@@ -957,12 +957,12 @@ static int rebuild_impl(PedoniModel* m) {
         if (total > 0) {
             {
                 ScopedTimer t(m, kScatter, s);
-                scatter_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm);
+                scatter_kernel<<<div_up(total, kScatterTile), kSortThreads, 0, s>>>(in, total, m->d_cell_start, m->d_perm);
                 m->launches += 1;
             }
             {
                 ScopedTimer t(m, kGather, s);
-                gather_kernel<<<div_up(total, 256), 256, 0, s>>>(in, total, m->d_cell_start, m->d_perm,
+                gather_kernel<<<div_up(total, kGatherTile), kSortThreads, 0, s>>>(in, total, m->d_cell_start, m->d_perm,
                                                                 m->buf[m->cur ^ 1]);
                 m->launches += 1;
             }

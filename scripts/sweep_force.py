@@ -3,6 +3,7 @@
 on a GPU box, time each with bench.py (kernel_ms_per_step.force). Usage:
     python scripts/sweep_force.py build            # here (nvcc cross-compiles)
     python scripts/sweep_force.py run [--agents N] # on the B200, via gpurun
+`--set sort` sweeps the elements per thread of the rebuild's scan / scatter / gather kernels instead.
 """
 import json
 import os
@@ -24,6 +25,9 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
+SORT_VARIANTS = {"base": [], "scan8": ["-DPEDONI_SCAN_ITEMS=8"], "scan32": ["-DPEDONI_SCAN_ITEMS=32"]}
+if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
+    VARIANTS = SORT_VARIANTS
 OUT = ROOT / "build" / "variants"
 
 
@@ -44,7 +48,9 @@ def main():
                                text=True)
             try:
                 d = json.loads(r.stdout.strip().splitlines()[-1])
-                print(f"{name:20s} force {d['kernel_ms_per_step']['force']:.4f} ms  step {d['ms_per_step']:.4f} ms", flush=True)
+                k = d["kernel_ms_per_step"]
+                print(f"{name:20s} step {d['ms_per_step']:.4f} ms  " + "  ".join(f"{n} {v:.4f}" for n, v in k.items()),
+                      flush=True)
             except Exception:
                 print(name, "FAILED", r.stderr[-400:], flush=True)
 

@@ -98,3 +98,27 @@ def test_capacity_growth_under_inflow(hall):
     np.testing.assert_array_equal(cd, od)
     assert np.nanmax(np.abs(cp - op)) <= 1e-3  # 12 ticks at ~7 ped/m^2
     cu.close()
+
+
+def test_cell_table_beyond_1024_scan_tiles():
+    """17.8 M cells = 1 085 scan tiles: the tile prefix sums more predecessors than a block has threads, and
+    tiles outnumber the resident CTAs several times over."""
+    from pedoni_b200.synthetic import SyntheticCrowd
+    crowd = SyntheticCrowd(n=120_000, density=120_000 / 5900.0 ** 2, field_unit=2.0)
+    sc, field = crowd.scenario(), crowd.field()
+    assert crowd.cells_per_side ** 2 > 1024 * 16384
+    pos, dest, vel, v0 = crowd.agents()
+    cu, orc = helpers.make_pair(sc, field, math_mode=PEDONI_MATH_FAST)
+    cu.upload_state(pos, dest, vel, v0)
+    orc.set(pos, dest, vel, v0)
+    for _ in range(3):
+        cu.rebuild()
+        orc.spawn()
+        assert cu.get_pedestrian_count() == orc.count()
+        np.testing.assert_array_equal(cu.cell_table(), orc.indices())
+        cu.step()
+        orc.update()
+    (cp, cd, _, _), (op, od, _, _) = cu.download(), orc.get()
+    np.testing.assert_array_equal(cd, od)
+    assert np.nanmax(np.abs(cp - op)) <= 4 * np.spacing(np.float32(5900.0))  # coordinates up to 5.9 km: 1 ulp = 4.9e-4
+    cu.close()
