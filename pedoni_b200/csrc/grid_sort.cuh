@@ -387,8 +387,8 @@ __device__ __forceinline__ void gather_one(const SortInput& in, uint32_t t, cons
     const Located l = locate(in, t);
     if (!l.live) return;
     const uint32_t idx = l.idx;
-    if (l.ticket[idx] == kKeyDrop) return;
     const uint32_t key = l.keys[idx];
+    if (key >= kKeyFirstSpecial) return;  // count_key: exactly the entries whose ticket is kKeyDrop
     const uint32_t begin = cell_start[key], end = cell_start[key + 1];
     uint32_t rank = 0;
     for (uint32_t j = begin; j < end; ++j) rank += (perm[j] < t) ? 1u : 0u;
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(kSortThreads) gather_kernel(SortInput in, uint
         if (t < total_upper) {
             const Located l = locate(in, t);
             if (l.live) {
-                keep[k] = l.ticket[l.idx] != kKeyDrop;
                 key[k] = l.keys[l.idx];
+                keep[k] = key[k] < kKeyFirstSpecial;  // count_key: exactly the entries that hold a ticket
                 pos[k] = l.a.pos[l.idx];
                 vel[k] = l.a.vel[l.idx];
                 v0[k] = l.a.v0[l.idx];
