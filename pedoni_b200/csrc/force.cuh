@@ -69,9 +69,9 @@ constexpr int kForceWarps = kForceThreads / 32;
 constexpr int kTileEntries = PEDONI_TILE_ENTRIES;  // agents per WARP tile: 3 windows of ~(32 + 2 cells) agents (~108 at 1 ped/m^2)
 constexpr int kListDepth = PEDONI_LIST_DEPTH;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
 constexpr int kTileAlloc = kTileEntries + 2;  // +1 spare slot for the scan's read-ahead, +1 keeps 16-byte alignment
-constexpr size_t kWarpSmemBytes = 2 * sizeof(float2) * kTileAlloc + sizeof(uint16_t) * kListDepth * 32;
+constexpr size_t kWarpSmemBytes = 2 * sizeof(float2) * kTileAlloc + sizeof(uint16_t) * (kListDepth + 1) * 32;  // +1 row: see pair_forces_tiled
 constexpr size_t kForceSmemBytes = kWarpSmemBytes * kForceWarps;
-static_assert(kTileEntries <= 65536, "list entries are 16-bit tile indices");
+static_assert(kWarpSmemBytes * (kForceThreads / 32) + 2048 <= 65536, "list entries are 16-bit addresses in the CTA's shared window");
 static_assert(kWarpSmemBytes % 16 == 0, "warp slices stay 16-byte aligned");
 
 struct ForceParams {
@@ -262,49 +262,118 @@ __device__ __forceinline__ void field_gradient(const float* __restrict__ g, int 
 }
 
 // Pair repulsion of one agent against its three candidate ranges held in the shared-memory tile
-// (sfm.rs:112-156). cur/stop are TILE indices. Rounds of SCAN (branch-free: one LDS.64, the cut-off
-// test in IEEE ops so the neighbor SET is exact in both modes, an unconditional 16-bit store and a
-// predicated advance) and FORCE (the converged heavy loop, two neighbours in flight for ILP, summed in
-// index order). A round scans at most as many candidates as the list has free slots, so any density
-// works; at 1 ped/m^2 one round covers everything.
+// (sfm.rs:112-156). cur/stop are TILE indices. Rounds of SCAN (branch-free: the cut-off test in IEEE ops so
+// the neighbor SET is exact in both modes, an unconditional 16-bit store and a predicated advance of the
+// write position) and FORCE (the converged heavy loop, two neighbours in flight for ILP, summed in index
+// order). A round scans at most as many candidates as the list has free slots, so any density works; at
+// 1 ped/m^2 one round covers everything.
+//
+// Everything is addressed by 32-bit addresses in the CTA's shared window (LDS/STS with immediate
+// displacements) and the list holds the address of the neighbour's tile entry (16 bits are enough: a CTA owns
+// ~21 KB), so neither loop spends instructions turning indices into addresses. SCAN takes two candidates per iteration
+// (rows hold ~6 per lane, ~9 per warp): the second one is masked off past the end of the range; its
+// unconditional store may land one slot past the list (hence kListDepth + 1 rows) and its read one entry
+// past the range (the tile has a spare entry).
+__device__ __forceinline__ float2 lds_f2(uint32_t sa) {  // sa: address in the shared window
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sa));
+    return v;
+}
+template <uint32_t kDelta>
+__device__ __forceinline__ float2 lds_f2_at(uint32_t sa) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(sa), "n"(kDelta));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t sa) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sa));
+    return v;
+}
+
+// SCAN of the two candidates at shared addresses sa and sa + 8 (sfm.rs:130-135): squared distance in IEEE
+// ops (packed: sub, mul, then one add), `!(d2 > 4)` (true for NaN, like the reference's `continue` on `>`),
+// the second candidate masked off at sa_end, `self` excluded in the middle row. Each candidate's address is
+// stored at the write position unconditionally and the position advances by one row if it is in range.
+// Written in PTX because the compiler's version of this loop carried three induction variables, a 16-bit
+// shadow of the index and select + add instead of a predicated add: 19 instructions per candidate, now ~10.
+#define PEDONI_SCAN_PAIR_ASM(SELF_TEST)                                                                       \
+    asm volatile(                                                                                             \
+        "{\n\t"                                                                                               \
+        ".reg .pred p0, p1;\n\t"                                                                              \
+        ".reg .b64 q0, q1;\n\t"                                                                               \
+        ".reg .f32 a0, b0, a1, b1;\n\t"                                                                       \
+        ".reg .b16 h0, h1;\n\t"                                                                               \
+        ".reg .u32 s1;\n\t"                                                                                   \
+        "ld.shared.b64 q0, [%1];\n\t"                                                                         \
+        "ld.shared.b64 q1, [%1+8];\n\t"                                                                       \
+        "add.u32 s1, %1, 8;\n\t"                                                                              \
+        "sub.rn.f32x2 q0, %3, q0;\n\t"                                                                        \
+        "sub.rn.f32x2 q1, %3, q1;\n\t"                                                                        \
+        "mul.rn.f32x2 q0, q0, q0;\n\t"                                                                        \
+        "mul.rn.f32x2 q1, q1, q1;\n\t"                                                                        \
+        "mov.b64 {a0, b0}, q0;\n\t"                                                                           \
+        "mov.b64 {a1, b1}, q1;\n\t"                                                                           \
+        "add.rn.f32 a0, a0, b0;\n\t"                                                                          \
+        "add.rn.f32 a1, a1, b1;\n\t"                                                                          \
+        "setp.lt.u32 p1, s1, %2;\n\t"                                                                         \
+        "setp.leu.f32 p0, a0, 0f40800000;\n\t"                                                                \
+        "setp.leu.and.f32 p1, a1, 0f40800000, p1;\n\t" SELF_TEST                                              \
+        "cvt.u16.u32 h0, %1;\n\t"                                                                             \
+        "cvt.u16.u32 h1, s1;\n\t"                                                                             \
+        "st.shared.u16 [%0], h0;\n\t"                                                                         \
+        "@p0 add.u32 %0, %0, 64;\n\t"                                                                         \
+        "st.shared.u16 [%0], h1;\n\t"                                                                         \
+        "@p1 add.u32 %0, %0, 64;\n\t"                                                                         \
+        "}"                                                                                                   \
+        : "+r"(wp)                                                                                            \
+        : "r"(sa), "r"(sa_end), "l"(pos2), "r"(self_sa)                                                       \
+        : "memory")
+
+template <bool kExcludeSelf>
+__device__ __forceinline__ void scan_pair(uint32_t sa, uint32_t sa_end, uint32_t self_sa, f32x2 pos2, uint32_t& wp) {
+    if (kExcludeSelf)
+        PEDONI_SCAN_PAIR_ASM("setp.ne.and.u32 p0, %1, %4, p0;\n\tsetp.ne.and.u32 p1, s1, %4, p1;\n\t");
+    else
+        PEDONI_SCAN_PAIR_ASM("");
+}
+#undef PEDONI_SCAN_PAIR_ASM
+
+// One row range of one lane: scan from cur up to stop or until the list is full (`more`).
+template <bool kExcludeSelf>
+__device__ __forceinline__ void scan_row(uint32_t& cur, uint32_t stop, uint32_t tile_sa, uint32_t col_sa, uint32_t self_sa,
+                                         f32x2 pos2, uint32_t& wp, bool& more) {
+    if (more) return;
+    const uint32_t room = (col_sa + static_cast<uint32_t>(kListDepth) * 64u - wp) / 64u;
+    const uint32_t lim = min(stop, cur + room);
+    const uint32_t sa_end = tile_sa + lim * 8u;
+#pragma unroll 1
+    for (uint32_t sa = tile_sa + cur * 8u; sa < sa_end; sa += 16u) scan_pair<kExcludeSelf>(sa, sa_end, self_sa, pos2, wp);
+    cur = lim;
+    more = lim < stop;
+}
+
 template <Math M>
-__device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, const float2* __restrict__ tile_pos,
-                                                  const float2* __restrict__ tile_vel, uint16_t* __restrict__ list,
+__device__ __forceinline__ void pair_forces_tiled(float2 pos, float2 e, uint32_t tile_sa, uint32_t col_sa,
                                                   uint32_t (&cur)[3], const uint32_t (&stop)[3], uint32_t self,
                                                   float2& acc) {
-    uint16_t* const col = list + (threadIdx.x & 31);  // this lane's column: col[k * 32]
+    constexpr uint32_t kSlot = 32u * sizeof(uint16_t);           // one list row: a 16-bit entry per lane (the 64 in scan_pair)
+    constexpr uint32_t kVelDelta = sizeof(float2) * kTileAlloc;  // tile_vel entry = tile_pos entry + this
+    static_assert(kSlot == 64, "scan_pair advances the write position by 64 bytes");
     const f32x2 pos2 = pack2(pos);
+    const uint32_t self_sa = tile_sa + self * 8u;
     bool more;
     do {
-        uint32_t cnt = 0;
+        uint32_t wp = col_sa;  // this lane's next free list slot
         more = false;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            if (more) continue;
-            uint32_t c = cur[d];
-            const uint32_t lim = min(stop[d], c + (static_cast<uint32_t>(kListDepth) - cnt));
-            // Rows hold ~6 candidates: keep the loop rolled (an unrolled-by-4 body with its remainder
-            // ladder costs more than it hides) and software-pipeline the tile read instead. Reading one
-            // entry past `lim` stays inside the warp's slice (the tile has a spare slot).
-            float2 po = tile_pos[c];
-#pragma unroll 1
-            for (; c < lim; ++c) {
-                const float2 nxt = tile_pos[c + 1];
-                const f32x2 dv = sub2(pos2, pack2(po));  // sfm.rs:131-135, IEEE per component
-                const float2 dd = unpack2(mul2(dv, dv));
-                bool ok = !(S::add(dd.x, dd.y) > 4.0f);
-                if (d == 1) ok = ok && (c != self);  // sfm.rs:130
-                col[cnt * 32] = static_cast<uint16_t>(c);
-                cnt += ok ? 1u : 0u;
-                po = nxt;
-            }
-            cur[d] = c;
-            more = c < stop[d];
-        }
+        scan_row<false>(cur[0], stop[0], tile_sa, col_sa, self_sa, pos2, wp, more);
+        scan_row<true>(cur[1], stop[1], tile_sa, col_sa, self_sa, pos2, wp, more);
+        scan_row<false>(cur[2], stop[2], tile_sa, col_sa, self_sa, pos2, wp, more);
 #pragma unroll kForceUnroll
-        for (uint32_t k = 0; k < cnt; ++k) {
-            const uint32_t c = col[k * 32];
-            PairTerm<(PEDONI_FAST_PAIR ? M : Math::Strict)>::add(pos, e, tile_pos[c], tile_vel[c], acc);
+        for (uint32_t r = col_sa; r < wp; r += kSlot) {
+            const uint32_t o = lds_u16(r);
+            const float2 po = lds_f2(o), vo = lds_f2_at<kVelDelta>(o);
+            PairTerm<(PEDONI_FAST_PAIR ? M : Math::Strict)>::add(pos, e, po, vo, acc);
         }
     } while (more);
 }
@@ -340,7 +409,6 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* tile_pos = reinterpret_cast<float2*>(smem_raw + kWarpSmemBytes * warp);
     float2* tile_vel = tile_pos + kTileAlloc;
-    uint16_t* list = reinterpret_cast<uint16_t*>(tile_vel + kTileAlloc);
 
     const uint32_t begin = p.d_range[0], end = p.d_range[1];
     const uint32_t block_first = begin + blockIdx.x * kForceThreads;
@@ -439,7 +507,9 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
             const uint32_t off[3] = {w0, w1 - n0, w2 - n0 - n1};
             uint32_t cur[3] = {r_beg[0] - off[0], r_beg[1] - off[1], r_beg[2] - off[2]};
             const uint32_t stop[3] = {r_end[0] - off[0], r_end[1] - off[1], r_end[2] - off[2]};
-            pair_forces_tiled<M>(pos, e, tile_pos, tile_vel, list, cur, stop, id - off[1], acc);
+            const uint32_t tile_sa = static_cast<uint32_t>(__cvta_generic_to_shared(tile_pos));
+            const uint32_t col_sa = tile_sa + 2u * sizeof(float2) * kTileAlloc + 2u * lane;
+            pair_forces_tiled<M>(pos, e, tile_sa, col_sa, cur, stop, id - off[1], acc);
         } else {
             pair_forces_global<M>(pos, e, p.in.pos, p.in.vel, r_beg, r_end, id, acc);
         }
