@@ -284,6 +284,13 @@ int pedoni_slab_exchange_local(PedoniModel* const* models, int32_t n);
  * "nccl send/recv" (fallback, or PEDONI_SLAB_TRANSPORT=nccl), "in-process ...", or "none". */
 const char* pedoni_slab_transport(const PedoniModel* model);
 
+/* 1 if the force kernel reads the field maps through texture gathers (PEDONI_MATH_FAST handles keep a
+ * second copy of the maps tiled into one 2D CUDA array: four gathers instead of sixteen loads per 4x4
+ * footprint, same texel values, verified against the linear copy at creation), 0 if it uses plain loads
+ * (strict handles; no memory for the second copy; maps that do not tile into 32768 x 32768 texels;
+ * PEDONI_FIELD_TEXTURES=0). */
+int pedoni_field_textures(const PedoniModel* model);
+
 /* The halo capacity in effect (0 on a whole-domain handle). */
 int pedoni_halo_capacity(const PedoniModel* model, uint32_t* halo_capacity);
 

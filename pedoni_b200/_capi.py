@@ -108,6 +108,7 @@ SIGNATURES = {
     "pedoni_slab_exchange_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32]),
     "pedoni_slab_transport": (C.c_char_p, [C.c_void_p]),
     "pedoni_halo_capacity": (C.c_int, [C.c_void_p, c_u32_p]),
+    "pedoni_field_textures": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

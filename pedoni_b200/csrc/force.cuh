@@ -213,20 +213,53 @@ __device__ __forceinline__ float inv_length(float x, float y) {
 //     the pedestrian disappears). Without this guard evacuation.toml, whose spawn lines lie exactly on
 //     corridor mid-lines, kept 13 pedestrians the reference loses in the first tick (40 %-evacuation
 //     time 31.6 +- 1.8 s instead of 22.6 +- 1.2 s over 20 seeds; scripts/exp_fast_stats.py).
-template <Math M, bool WithCentre>
-__device__ __forceinline__ void field_gradient(const float* __restrict__ g, int ny, int nx, float2 q, float noise_limit,
-                                               float flat_limit2, float& gx, float& gy, float& centre) {
+//
+// kTex: the 4x4 footprint comes from four texture gathers instead of sixteen loads. The kernel is bound by
+// the L1 data pipe (92 % busy: ncu, profiles/r01g_force_10M_full.md), and sixteen 4-byte loads with one
+// address per lane cost ~8 wavefronts each; a gather returns a 2x2 block per lane and request. Same texel
+// values, so everything downstream is unchanged.
+//
+// tld4 returns the 2x2 block a bilinear fetch at the given coordinate would blend, as (x, y, z, w) =
+// texels (i, j+1), (i+1, j+1), (i+1, j), (i, j). With unnormalised coordinates texel i covers [i, i+1),
+// so the block whose lower texel is (i, j) is addressed at (i + 1, j + 1): half a texel away from any
+// switch-over, exact in fp32. All maps live in one atlas so that the whole warp uses ONE texture handle: with
+// a handle per destination the compiler wraps every tld4 in a loop over the distinct handles of the warp.
+// pedoni_create verifies this layout against plain loads on the actual maps before it enables the path
+// (footprint_check_kernel).
+__device__ __forceinline__ void footprint_gather(cudaTextureObject_t tex, int x0, int y0, float (&t)[4][4]) {
+    const float fx = static_cast<float>(x0) + 1.0f, fy = static_cast<float>(y0) + 1.0f;
+#pragma unroll
+    for (int by = 0; by < 2; ++by)
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx) {
+            const float4 g = tex2Dgather<float4>(tex, fx + 2.0f * bx, fy + 2.0f * by, 0);
+            t[2 * by + 1][2 * bx] = g.x;
+            t[2 * by + 1][2 * bx + 1] = g.y;
+            t[2 * by][2 * bx + 1] = g.z;
+            t[2 * by][2 * bx] = g.w;
+        }
+}
+
+// `tile`: texel offset of the map inside the atlas (kTex only).
+template <Math M, bool WithCentre, bool kTex>
+__device__ __forceinline__ void field_gradient(const float* __restrict__ g, cudaTextureObject_t tex, int2 tile, int ny, int nx,
+                                               float2 q, float noise_limit, float flat_limit2, float& gx, float& gy,
+                                               float& centre) {
     if (M == Math::Fast && PEDONI_FAST_FIELD) {
         const float bx = floorf(q.x), by = floorf(q.y);
         const int x0 = __float2int_rz(bx) - 1, y0 = __float2int_rz(by) - 1;
         if (x0 >= 0 && y0 >= 0 && x0 + 3 < nx && y0 + 3 < ny) {
             const float tx = q.x - bx, ty = q.y - by, sx = 1.0f - tx, sy = 1.0f - ty;
-            const float* base = g + static_cast<size_t>(y0) * nx + x0;
             float t[4][4];
+            if (kTex) {
+                footprint_gather(tex, x0 + tile.x, y0 + tile.y, t);
+            } else {
+                const float* base = g + static_cast<size_t>(y0) * nx + x0;
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) t[r][c] = __ldg(base + static_cast<size_t>(r) * nx + c);
+                    for (int c = 0; c < 4; ++c) t[r][c] = __ldg(base + static_cast<size_t>(r) * nx + c);
+            }
             // (The max over all 16 texels also keeps the 16 loads in flight together: testing a single
             // central texel is 15 instructions shorter and measurably SLOWER, 0.846 vs 0.809 ms at 10 M.)
             float big = 0.0f;
@@ -401,9 +434,10 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <Math M, bool kDistanceMap>
+template <Math M, bool kDistanceMap, bool kTex>
 __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_MIN_BLOCKS : PEDONI_FORCE_MIN_BLOCKS_STRICT)
     force_integrate_kernel(ForceParams p) {
+    static_assert(!(kTex && M == Math::Strict), "strict math never reads the maps through textures");
     using O = Ops<M>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -482,16 +516,21 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
         const float flat_limit2 = (8.0e-3f * p.field.unit) * (8.0e-3f * p.field.unit);
         float gx, gy, unused;
         // dest < n_maps is guaranteed by the rebuild that admitted this agent (sort_key).
-        field_gradient<M, false>(p.field.potential_maps + static_cast<size_t>(dest) * p.field.fy * p.field.fx,
-                                 p.field.fy, p.field.fx, q, noise_limit, flat_limit2, gx, gy, unused);
+        int2 tile = make_int2(0, 0);
+        if (kTex) {
+            const int t = 1 + static_cast<int>(dest);
+            tile = make_int2((t % p.field.atlas_tiles_x) * p.field.fx, (t / p.field.atlas_tiles_x) * p.field.fy);
+        }
+        field_gradient<M, false, kTex>(p.field.potential_maps + static_cast<size_t>(dest) * p.field.fy * p.field.fx,
+                                       p.field.atlas, tile, p.field.fy, p.field.fx, q, noise_limit, flat_limit2, gx, gy, unused);
         const float rlen = inv_length<M>(gx, gy);
         e = make_float2(O::mul(gx, rlen), O::mul(gy, rlen));
         acc.x = O::add(acc.x, O::div(O::sub(O::mul(e.x, v0), vel.x), 0.5f));  // x / 0.5 == x * 2 exactly
         acc.y = O::add(acc.y, O::div(O::sub(O::mul(e.y, v0), vel.y), 0.5f));
         if (kDistanceMap) {
             float dgx, dgy, distance;
-            field_gradient<M, true>(p.field.distance_map, p.field.fy, p.field.fx, q, noise_limit, flat_limit2, dgx, dgy,
-                                    distance);
+            field_gradient<M, true, kTex>(p.field.distance_map, p.field.atlas, make_int2(0, 0), p.field.fy, p.field.fx, q,
+                                          noise_limit, flat_limit2, dgx, dgy, distance);
             const float rl = inv_length<M>(dgx, dgy);
             const float coef = O::mul(10.0f * 0.2f, O::exp(O::div(-distance, 0.2f)));
             wall = make_float2(O::mul(coef, -O::mul(dgx, rl)), O::mul(coef, -O::mul(dgy, rl)));

@@ -57,6 +57,9 @@ struct PedoniModel {
     FieldView field{};
     float* d_distance = nullptr;
     float* d_potential = nullptr;
+    // fast math: the maps once more, tiled into one 2D CUDA array behind a point-sampled texture (FieldView::atlas)
+    cudaArray_t field_atlas = nullptr;
+    bool field_tex = false;
     float* d_edges = nullptr;
     int n_obstacles = 0;
     uint32_t n_cells = 0;  // local table cells
@@ -393,9 +396,9 @@ SortInput make_sort_input(PedoniModel* m) {
     return in;
 }
 
-template <Math M, bool D>
+template <Math M, bool D, bool T>
 void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem, cudaStream_t s) {
-    force_integrate_kernel<M, D><<<blocks, kForceThreads, smem, s>>>(p);
+    force_integrate_kernel<M, D, T><<<blocks, kForceThreads, smem, s>>>(p);
     m->launches += 1;
 }
 
@@ -423,14 +426,19 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     ScopedTimer t(m, kForce, s, count_upper);
     if (m->math_mode == PEDONI_MATH_STRICT) {
         if (m->use_distance_map)
-            launch_force_t<Math::Strict, true>(m, p, blocks, smem, s);
+            launch_force_t<Math::Strict, true, false>(m, p, blocks, smem, s);
         else
-            launch_force_t<Math::Strict, false>(m, p, blocks, smem, s);
+            launch_force_t<Math::Strict, false, false>(m, p, blocks, smem, s);
+    } else if (m->field_tex) {
+        if (m->use_distance_map)
+            launch_force_t<Math::Fast, true, true>(m, p, blocks, smem, s);
+        else
+            launch_force_t<Math::Fast, false, true>(m, p, blocks, smem, s);
     } else {
         if (m->use_distance_map)
-            launch_force_t<Math::Fast, true>(m, p, blocks, smem, s);
+            launch_force_t<Math::Fast, true, false>(m, p, blocks, smem, s);
         else
-            launch_force_t<Math::Fast, false>(m, p, blocks, smem, s);
+            launch_force_t<Math::Fast, false, false>(m, p, blocks, smem, s);
     }
 }
 
@@ -571,6 +579,84 @@ int setup_peer_transport(PedoniModel* m) {
     cudaFree(d_ok);
     m->transport = ok ? PedoniModel::kTransportPeer : PedoniModel::kTransportNccl;
     return PEDONI_OK;
+}
+
+// ---- field maps as one texture atlas (fast math) -------------------------------------------------------
+// Footprints at pseudo-random places of every map, fetched with footprint_gather and with plain loads: any
+// difference (a gather component order or a coordinate convention other than the one force.cuh assumes)
+// raises the flag and the handle keeps the load path.
+__global__ void footprint_check_kernel(FieldView f, uint32_t* mismatch) {
+    const int map = blockIdx.y;  // 0: distance map, 1 + k: potential map k
+    const unsigned long long r = splitmix64((static_cast<unsigned long long>(map) << 32) | (blockIdx.x * blockDim.x + threadIdx.x));
+    const int x0 = static_cast<int>((r & 0xFFFFFFFFull) % static_cast<unsigned>(f.fx - 3));
+    const int y0 = static_cast<int>((r >> 32) % static_cast<unsigned>(f.fy - 3));
+    const float* g = map == 0 ? f.distance_map : f.potential_maps + static_cast<size_t>(map - 1) * f.fy * f.fx;
+    float t[4][4];
+    footprint_gather(f.atlas, x0 + (map % f.atlas_tiles_x) * f.fx, y0 + (map / f.atlas_tiles_x) * f.fy, t);
+    bool same = true;
+    for (int r4 = 0; r4 < 4; ++r4)
+        for (int c4 = 0; c4 < 4; ++c4)
+            same = same && __float_as_uint(t[r4][c4]) == __float_as_uint(g[static_cast<size_t>(y0 + r4) * f.fx + x0 + c4]);
+    if (!same) atomicOr(mismatch, 1u);
+}
+
+void release_field_textures(PedoniModel* m) {
+    if (m->field.atlas) cudaDestroyTextureObject(m->field.atlas);
+    if (m->field_atlas) cudaFreeArray(m->field_atlas);
+    m->field_atlas = nullptr;
+    m->field.atlas = 0;
+    m->field_tex = false;
+}
+
+// Builds the atlas + texture object from the device copies of the maps and verifies it. Any failure (no
+// memory for a second copy, maps that do not tile into a 32768 x 32768 gather array, unexpected gather
+// layout) leaves the handle on the load path: slower, same results. PEDONI_FIELD_TEXTURES=0 skips the attempt.
+void build_field_textures(PedoniModel* m) {
+    const char* env = std::getenv("PEDONI_FIELD_TEXTURES");
+    if (env && env[0] == '0') return;
+    constexpr int kMaxGather = 32768;  // cudaDeviceProp::maxTexture2DGather
+    const int fx = m->field.fx, fy = m->field.fy, n = 1 + m->field.n_maps;
+    if (fx < 4 || fy < 4 || fx > kMaxGather || fy > kMaxGather) return;
+    const int tiles_x = std::min(n, kMaxGather / fx), tiles_y = (n + tiles_x - 1) / tiles_x;
+    if (static_cast<long long>(tiles_y) * fy > kMaxGather) return;
+    const size_t map_elems = static_cast<size_t>(fx) * fy;
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+    bool ok = cudaMallocArray(&m->field_atlas, &desc, static_cast<size_t>(tiles_x) * fx, static_cast<size_t>(tiles_y) * fy,
+                              cudaArrayTextureGather) == cudaSuccess;
+    for (int k = 0; k < n && ok; ++k) {
+        const float* src = k == 0 ? m->d_distance : m->d_potential + static_cast<size_t>(k - 1) * map_elems;
+        ok = cudaMemcpy2DToArrayAsync(m->field_atlas, sizeof(float) * (k % tiles_x) * fx, static_cast<size_t>(k / tiles_x) * fy, src,
+                                      sizeof(float) * fx, sizeof(float) * fx, fy, cudaMemcpyDeviceToDevice,
+                                      m->stream) == cudaSuccess;
+    }
+    if (ok) {
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = m->field_atlas;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;  // never exercised: footprints are in bounds
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        ok = cudaCreateTextureObject(&m->field.atlas, &res, &td, nullptr) == cudaSuccess;
+        m->field.atlas_tiles_x = tiles_x;
+    }
+    uint32_t* d_flag = nullptr;
+    uint32_t flag = 1;
+    if (ok) ok = cudaMalloc(&d_flag, sizeof(uint32_t)) == cudaSuccess;
+    if (ok) {
+        cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), m->stream);
+        footprint_check_kernel<<<dim3(8, n), 128, 0, m->stream>>>(m->field, d_flag);
+        ok = cudaMemcpyAsync(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost, m->stream) == cudaSuccess &&
+             cudaStreamSynchronize(m->stream) == cudaSuccess && flag == 0;
+    }
+    if (d_flag) cudaFree(d_flag);
+    if (!ok) {
+        cudaGetLastError();  // an optimisation that did not fit is not an error of the handle
+        release_field_textures(m);
+        return;
+    }
+    m->field_tex = true;
 }
 
 }  // namespace
@@ -729,6 +815,7 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
                                cudaMemcpyHostToDevice, m->stream));
     m->field.distance_map = m->d_distance;
     m->field.potential_maps = m->d_potential;
+    if (m->math_mode == PEDONI_MATH_FAST) build_field_textures(m);
 
     m->n_obstacles = c->n_obstacles;
     if (!m->use_distance_map && m->n_obstacles > 0) {
@@ -789,6 +876,7 @@ void pedoni_destroy(PedoniModel* m) {
     for (auto e : m->event_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : {m->timer_start, m->timer_stop, m->ev_packed, m->ev_halo, m->ev_edge, m->ev_peer})
         if (e) cudaEventDestroy(e);
+    release_field_textures(m);
     free_agents(m->buf[0]);
     free_agents(m->buf[1]);
     free_agents(m->app);
@@ -1401,6 +1489,8 @@ const char* pedoni_slab_transport(const PedoniModel* m) {
         default: return "in-process (pedoni_slab_exchange_local)";
     }
 }
+int pedoni_field_textures(const PedoniModel* m) { return m && m->field_tex ? 1 : 0; }
+
 int pedoni_halo_capacity(const PedoniModel* m, uint32_t* halo_capacity) {
     if (!m || !halo_capacity) return PEDONI_ERR_INVALID;
     *halo_capacity = m->halo_cap;

@@ -95,6 +95,13 @@ struct FieldView {
     int n_maps;
     const float* __restrict__ distance_map;
     const float* __restrict__ potential_maps;
+    // The same maps once more, tiled into ONE point-sampled 2D CUDA array (an atlas: one texture handle for
+    // the whole warp) for the force kernel's 4x4 footprints (texture gather, see footprint_gather in
+    // force.cuh). Tile 0 is the distance map, tile 1 + k potential map k; tile t sits at texel
+    // ((t % atlas_tiles_x) * fx, (t / atlas_tiles_x) * fy). atlas == 0: not available (strict handles never
+    // make one).
+    cudaTextureObject_t atlas;
+    int atlas_tiles_x;
 };
 
 __device__ __forceinline__ float field_tap(const float* __restrict__ g, int ny, int nx, int x, int y) {

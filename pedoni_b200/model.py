@@ -233,6 +233,10 @@ class SocialForceModelCuda:
     def slab_transport(self) -> str:
         return self._lib.pedoni_slab_transport(self._h).decode()
 
+    def field_textures(self) -> bool:
+        """True if the force kernel fetches the field maps with texture gathers (fast math only)."""
+        return bool(self._lib.pedoni_field_textures(self._h))
+
     def halo_capacity(self) -> int:
         h = C.c_uint32()
         _capi.check(self._lib.pedoni_halo_capacity(self._h, C.byref(h)), self._h)

@@ -25,7 +25,7 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
-SORT_VARIANTS = {"base": [], "scan8": ["-DPEDONI_SCAN_ITEMS=8"], "scan32": ["-DPEDONI_SCAN_ITEMS=32"]}
+SORT_VARIANTS = {"base": [], "fewer_taps": ["-DPEDONI_EXP_FEWER_TAPS"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
 OUT = ROOT / "build" / "variants"

@@ -199,3 +199,29 @@ def test_published_count_trails_but_never_blocks(corridor):
     assert n + 0 >= cu.get_pedestrian_count() > 0
     assert all(a[1] <= b[1] for a, b in zip(seen, seen[1:])) and seen[-1][1] <= ordinal
     cu.close()
+
+
+def test_texture_gather_path_is_bit_identical_to_loads(corridor, monkeypatch):
+    """Fast math fetches the 4x4 field footprints with texture gathers when the handle could build the 2D
+    arrays (pedoni_field_textures); the texel values are the same, so ten ticks must agree bit for bit with
+    a handle forced onto plain loads."""
+    sc, field = corridor
+    from pedoni_b200 import SocialForceModelCuda
+    pos, dest, vel, v0 = helpers.random_crowd(4000, sc.field.size, seed=11, margin=2.0)
+    outs = []
+    for knob in ("1", "0"):
+        monkeypatch.setenv("PEDONI_FIELD_TEXTURES", knob)
+        cu = SocialForceModelCuda(SimulatorOptions(), sc, field, math_mode=PEDONI_MATH_FAST)
+        assert cu.field_textures() == (knob == "1")
+        cu.upload_state(pos, dest, vel, v0)
+        for _ in range(10):
+            cu.rebuild()
+            cu.step()
+        outs.append(cu.download())
+        cu.close()
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(bits(a), bits(b))
+    monkeypatch.setenv("PEDONI_FIELD_TEXTURES", "1")
+    strict = SocialForceModelCuda(SimulatorOptions(), sc, field, math_mode=PEDONI_MATH_STRICT)
+    assert not strict.field_textures()
+    strict.close()
