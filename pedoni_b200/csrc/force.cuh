@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     p.out.dest[id] = dest;
     // ghost-row agents are integrated twice (here and by their owner): only the owner counts an arrival
     const bool owned = id >= p.d_owned[0] && id < p.d_owned[1];
-    count_key(sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned), p.cell_count, p.keys_out + id,
+    count_key(sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned, kTex), p.cell_count, p.keys_out + id,
               p.ticket_out + id);
     // Slab handles exchange two ghost rows per tick, which covers every move of less than one grid row
     // (1.4 m per 0.1 s); anything faster would silently vanish at a slab boundary, so flag it.

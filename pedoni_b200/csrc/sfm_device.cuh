@@ -147,8 +147,19 @@ __device__ __forceinline__ float2 field_coord(float2 pos, const FieldView& f) {
 }
 
 // field.rs:235-239
-__device__ __forceinline__ float get_potential(const FieldView& f, uint32_t waypoint, float2 pos) {
+__device__ __forceinline__ float get_potential(const FieldView& f, uint32_t waypoint, float2 pos, bool use_atlas = false) {
     float2 q = field_coord(pos, f);
+    if (use_atlas) {
+        // the 2x2 footprint of a bilinear sample is exactly one texture gather on the atlas (component
+        // order: see footprint_gather in force.cuh); same texels, same combine -> same bits
+        const Axis ax = axis_of(q.x), ay = axis_of(q.y);
+        if (ax.i >= 0 && ay.i >= 0 && ax.i + 1 < f.fx && ay.i + 1 < f.fy) {
+            const int t = 1 + static_cast<int>(waypoint);
+            const float4 g = tex2Dgather<float4>(f.atlas, static_cast<float>((t % f.atlas_tiles_x) * f.fx + ax.i) + 1.0f,
+                                                 static_cast<float>((t / f.atlas_tiles_x) * f.fy + ay.i) + 1.0f, 0);
+            return bilinear_combine(ax, ay, g.w, g.z, g.x, g.y);
+        }
+    }
     return bilinear(f.potential_maps + static_cast<size_t>(waypoint) * f.fy * f.fx, f.fy, f.fx, q.x, q.y);
 }
 
@@ -247,14 +258,14 @@ __device__ __forceinline__ int2 cell_of(float2 pos, float unit) {
 //    whose rows `count_arrival` says it belongs — the observable "flow" (SURVEY.md section 8, row f3).
 __device__ __forceinline__ uint32_t sort_key(const GridView& g, const FieldView& f, float2 pos, uint32_t dest,
                                              uint32_t* error_flag, unsigned long long* arrived = nullptr,
-                                             bool count_arrival = false) {
+                                             bool count_arrival = false, bool use_atlas = false) {
     int2 c = cell_of(pos, g.unit);
     if (c.x < 0 || c.y < 0 || c.x >= g.nx || c.y >= g.ny) return kKeyDrop;
     if (dest >= static_cast<uint32_t>(f.n_maps)) {
         atomicOr(error_flag, kErrBadDestination);
         return kKeyDrop;
     }
-    const float potential = get_potential(f, dest, pos);
+    const float potential = get_potential(f, dest, pos, use_atlas);
     if (!(potential > 0.25f)) {
         if (count_arrival && potential == potential) atomicAdd(arrived + min(dest, 15u), 1ull);
         return kKeyDrop;
