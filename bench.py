@@ -32,9 +32,9 @@ sys.path.insert(0, str(ROOT))
 
 ALGO_BYTES_PER_UPDATE = 48  # read 24 B state + write 24 B state
 # DRAM bytes the force kernel actually moves per update: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` launch at this workload (profiles/r01f_force_10M_full.md: 2.191 GB + 0.340 GB for
-# 9 997 570 pedestrians). The excess over 48 B is the field maps: two 4x4 texel footprints per pedestrian.
-NCU_TRAFFIC_BYTES_PER_UPDATE = (2.191440e9 + 339.557632e6) / 9997570
+# `ncu --set full` launch at this workload (profiles/r01i_force_10M_full.md: 2.094 GB + 0.343 GB for
+# 9 999 438 pedestrians). The excess over 48 B is the field maps: two 4x4 texel footprints per pedestrian.
+NCU_TRAFFIC_BYTES_PER_UPDATE = (2.093599e9 + 343.457536e6) / 9999438
 RELAX_STEPS = 50            # untimed: lets the zero-velocity seed crowd reach walking state
 E2E_SPAWN_PER_STEP = 1024   # host->device spawn batch per e2e step
 
@@ -348,6 +348,7 @@ def run_ours(args):
                        "density_per_m2": args.density, "neighbor_unit_m": 1.4, "field_unit_m": 0.25,
                        "math_mode": args.math, "decomposition": f"{world} row slab(s)",
                        "slab_transport": model.slab_transport(),
+                       "field_fetch": "texture gather (atlas)" if model.field_textures() else "global loads",
                        "relax_steps_untimed": args.relax, "active_pedestrians": int(updates_all / args.steps),
                        "l2": "inputs larger than L2 (2 x 24 B x N state + 3 field maps >> 126 MB); no flush"},
             "e2e": e2e,
@@ -356,7 +357,7 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES_PER_UPDATE * agents_per_launch
                                      if args.math == "fast" and args.density == 1.0 else None),
-                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01f_force_10M_full.md, "
+                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01i_force_10M_full.md, "
                                          "scaled by pedestrians per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
