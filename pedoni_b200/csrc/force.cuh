@@ -68,8 +68,14 @@ constexpr int kForceUnroll = PEDONI_FORCE_UNROLL;
 constexpr int kForceWarps = kForceThreads / 32;
 constexpr int kTileEntries = PEDONI_TILE_ENTRIES;  // agents per WARP tile: 3 windows of ~(32 + 2 cells) agents (~108 at 1 ped/m^2)
 constexpr int kListDepth = PEDONI_LIST_DEPTH;     // in-range neighbours per agent per round (mean 12 at 1 ped/m^2)
+#ifndef PEDONI_BULK_STAGE
+#define PEDONI_BULK_STAGE 1  // stage the tile with cp.async.bulk (TMA) instead of per-lane cp.async
+#endif
 constexpr int kTileAlloc = kTileEntries + 2;  // +1 spare slot for the scan's read-ahead, +1 keeps 16-byte alignment
-constexpr size_t kWarpSmemBytes = 2 * sizeof(float2) * kTileAlloc + sizeof(uint16_t) * (kListDepth + 1) * 32;  // +1 row: see pair_forces_tiled
+// two tiles (pos, vel) + the neighbour lists (+1 row: see pair_forces_tiled) + the warp's mbarrier
+constexpr size_t kWarpMbarOffset = 2 * sizeof(float2) * kTileAlloc + sizeof(uint16_t) * (kListDepth + 1) * 32;
+constexpr size_t kWarpSmemBytes = kWarpMbarOffset + 16;
+static_assert(kTileAlloc % 2 == 0 && kWarpSmemBytes % 16 == 0, "bulk copies need 16-byte aligned tiles");
 constexpr size_t kForceSmemBytes = kWarpSmemBytes * kForceWarps;
 static_assert(kWarpSmemBytes * (kForceThreads / 32) + 2048 <= 65536, "list entries are 16-bit addresses in the CTA's shared window");
 static_assert(kWarpSmemBytes % 16 == 0, "warp slices stay 16-byte aligned");
@@ -434,6 +440,34 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- bulk (TMA) staging: one mbarrier per warp, used for exactly one phase -----------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_sa), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar_sa, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar_sa, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(mbar_sa), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// global -> shared, 16-byte aligned on both sides, bytes a multiple of 16; completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_sa, const void* src, uint32_t bytes, uint32_t mbar_sa) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_sa),
+                 "l"(src), "r"(bytes), "r"(mbar_sa)
+                 : "memory");
+}
+
 template <Math M, bool kDistanceMap, bool kTex>
 __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_MIN_BLOCKS : PEDONI_FORCE_MIN_BLOCKS_STRICT)
     force_integrate_kernel(ForceParams p) {
@@ -443,6 +477,7 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* tile_pos = reinterpret_cast<float2*>(smem_raw + kWarpSmemBytes * warp);
     float2* tile_vel = tile_pos + kTileAlloc;
+    (void)tile_vel;  // only the cp.async staging variant names it
 
     const uint32_t begin = p.d_range[0], end = p.d_range[1];
     const uint32_t block_first = begin + blockIdx.x * kForceThreads;
@@ -457,6 +492,12 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     }
     const bool live = id < end;
     const int last_lane = warp_first < end ? static_cast<int>(min(32u, end - warp_first)) - 1 : 0;
+    const uint32_t tile_sa = static_cast<uint32_t>(__cvta_generic_to_shared(tile_pos));
+    const uint32_t mbar_sa = tile_sa + static_cast<uint32_t>(kWarpMbarOffset);
+    if (PEDONI_BULK_STAGE) {
+        if (lane == 0) mbar_init(mbar_sa, 1);
+        __syncwarp();
+    }
 
     float2 pos = make_float2(0.f, 0.f), vel = pos, e = pos, acc = pos;
     float v0 = 0.f;
@@ -494,6 +535,32 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
                    w2 = __shfl_sync(0xFFFFFFFFu, r_beg[2], 0);
     const uint32_t e0 = __shfl_sync(0xFFFFFFFFu, r_end[0], last_lane), e1 = __shfl_sync(0xFFFFFFFFu, r_end[1], last_lane),
                    e2 = __shfl_sync(0xFFFFFFFFu, r_end[2], last_lane);
+#if PEDONI_BULK_STAGE
+    // Windows rounded outward to even indices: both ends of a bulk copy must be 16-byte aligned (the arrays
+    // have two spare entries for this). a_d: first staged index, n_d: staged entries, window d starts at
+    // tile index n_0 + ... + n_{d-1}.
+    const uint32_t a0 = w0 & ~1u, a1 = w1 & ~1u, a2 = w2 & ~1u;
+    const uint32_t n0 = ((e0 + 1u) & ~1u) - a0, n1 = ((e1 + 1u) & ~1u) - a1, n2 = ((e2 + 1u) & ~1u) - a2;
+    const bool tiled = e0 >= w0 && e1 >= w1 && e2 >= w2 &&
+                       (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries);
+    if (tiled && lane == 0) {
+        constexpr uint32_t kVel = sizeof(float2) * kTileAlloc;
+        mbar_expect_tx(mbar_sa, (n0 + n1 + n2) * 16u);
+        if (n0) {
+            bulk_g2s(tile_sa, p.in.pos + a0, n0 * 8u, mbar_sa);
+            bulk_g2s(tile_sa + kVel, p.in.vel + a0, n0 * 8u, mbar_sa);
+        }
+        if (n1) {
+            bulk_g2s(tile_sa + n0 * 8u, p.in.pos + a1, n1 * 8u, mbar_sa);
+            bulk_g2s(tile_sa + kVel + n0 * 8u, p.in.vel + a1, n1 * 8u, mbar_sa);
+        }
+        if (n2) {
+            bulk_g2s(tile_sa + (n0 + n1) * 8u, p.in.pos + a2, n2 * 8u, mbar_sa);
+            bulk_g2s(tile_sa + kVel + (n0 + n1) * 8u, p.in.vel + a2, n2 * 8u, mbar_sa);
+        }
+    }
+#else
+    const uint32_t a0 = w0, a1 = w1, a2 = w2;
     const uint32_t n0 = e0 - w0, n1 = e1 - w1, n2 = e2 - w2;
     const bool tiled = e0 >= w0 && e1 >= w1 && e2 >= w2 &&
                        (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries);
@@ -504,6 +571,7 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
             cp_async_8(tile_vel + k, p.in.vel + i);
         }
     }
+#endif
 
     // ---- steering (sfm.rs:106-109; field.rs:248-252) and walls from the distance map (sfm.rs:188-192;
     // field.rs:242-245,255-258), evaluated while the tile copies are in flight.
@@ -536,17 +604,24 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
             wall = make_float2(O::mul(coef, -O::mul(dgx, rl)), O::mul(coef, -O::mul(dgy, rl)));
         }
     }
+#if PEDONI_BULK_STAGE
+    if (tiled) {  // bounded: a lost completion must not hang the GPU
+        uint32_t spins = 0;
+        while (!mbar_try_wait(mbar_sa, 0) && ++spins < (1u << 24)) {}
+        if (spins >= (1u << 24)) atomicOr(p.error_flag, kErrStageTimeout);
+    }
+#else
     cp_async_wait_all();
+#endif
     __syncwarp();
 
     // ---- pair repulsion (sfm.rs:112-156)
     if (live) {
         if (tiled) {
             // candidate c of row offset d sits at tile index c - off[d]
-            const uint32_t off[3] = {w0, w1 - n0, w2 - n0 - n1};
+            const uint32_t off[3] = {a0, a1 - n0, a2 - n0 - n1};
             uint32_t cur[3] = {r_beg[0] - off[0], r_beg[1] - off[1], r_beg[2] - off[2]};
             const uint32_t stop[3] = {r_end[0] - off[0], r_end[1] - off[1], r_end[2] - off[2]};
-            const uint32_t tile_sa = static_cast<uint32_t>(__cvta_generic_to_shared(tile_pos));
             const uint32_t col_sa = tile_sa + 2u * sizeof(float2) * kTileAlloc + 2u * lane;
             pair_forces_tiled<M>(pos, e, tile_sa, col_sa, cur, stop, id - off[1], acc);
         } else {

@@ -198,8 +198,9 @@ struct HVec2 {
 
 cudaError_t alloc_agents(AgentArrays& a, uint32_t cap) {
     cudaError_t e;
-    if ((e = cudaMalloc(&a.pos, sizeof(float2) * (size_t)cap)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&a.vel, sizeof(float2) * (size_t)cap)) != cudaSuccess) return e;
+    // + 2: the force kernel's bulk copies round their windows outward to 16-byte boundaries
+    if ((e = cudaMalloc(&a.pos, sizeof(float2) * ((size_t)cap + 2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&a.vel, sizeof(float2) * ((size_t)cap + 2))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&a.v0, sizeof(float) * (size_t)cap)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&a.dest, sizeof(uint32_t) * (size_t)cap)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -457,6 +458,8 @@ int check_device_error(PedoniModel* m) {
         return fail(m, PEDONI_ERR_CAPACITY,
                     "two boundary rows of a slab hold more than halo_capacity = %u agents (or the ghost strip "
                     "overran the arrays); raise PedoniConfig.halo_capacity", m->halo_cap);
+    if (bits & kErrStageTimeout)
+        return fail(m, PEDONI_ERR_CUDA, "force kernel: the bulk copies staging a warp's neighbour tile never completed");
     if (bits & kErrHaloTimeout)
         return fail(m, PEDONI_ERR_COMM,
                     "slab %d of %d waited 20 s for a neighbour's ghost strip (peer-memory transport): a rank died or "

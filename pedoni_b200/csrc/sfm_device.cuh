@@ -240,6 +240,7 @@ constexpr uint32_t kErrBadDestination = 1u;  // destination >= n_potential_maps 
 constexpr uint32_t kErrRowJump = 2u;         // slab handle: a pedestrian crossed >= 2 grid rows in one step
 constexpr uint32_t kErrHaloOverflow = 4u;    // slab handle: two boundary rows hold more agents than halo_capacity
 constexpr uint32_t kErrHaloTimeout = 8u;     // slab handle: a neighbour's strip did not arrive within 20 s
+constexpr uint32_t kErrStageTimeout = 16u;   // force kernel: a warp's bulk copies never completed (a bug, not a user error)
 
 // `(pos / unit).as_ivec2()` (neighbor_grid.rs:27, sfm.rs:113): IEEE divide, truncate toward zero.
 __device__ __forceinline__ int2 cell_of(float2 pos, float unit) {

@@ -25,7 +25,7 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
-SORT_VARIANTS = {"base": [], "fewer_taps": ["-DPEDONI_EXP_FEWER_TAPS"]}
+SORT_VARIANTS = {"base": [], "no_bulk": ["-DPEDONI_BULK_STAGE=0"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
 OUT = ROOT / "build" / "variants"
