@@ -170,9 +170,11 @@ int pedoni_download(PedoniModel* model, float* pos_xy, uint32_t* destination, fl
  * tick, main.rs:95). pedoni_download_begin snapshots (position, destination) of the owned pedestrians on
  * the device behind the work already enqueued and starts copying the snapshot to the caller's buffers
  * on a separate stream; it returns at once, and spawn / rebuild / step may be called meanwhile.
- * pedoni_download_end blocks until the copy has landed and reports how many pedestrians were written.
- * The buffers must stay valid (pinned memory makes the copy truly asynchronous) until _end returns; one
- * pipelined download may be in flight per handle. Needs a rebuilt state (no pending pedoni_spawn).
+ * pedoni_download_end blocks until the OLDEST copy in flight has landed and reports how many pedestrians
+ * were written. The buffers must stay valid (pinned memory makes the copy truly asynchronous) until the
+ * matching _end returns; up to two pipelined downloads may be in flight per handle (begin k, begin k+1,
+ * end k, ...: PCIe stays busy while _end finishes tick k on the host, see pedoni_download_wire_bytes).
+ * Needs a rebuilt state (no pending pedoni_spawn).
  */
 int pedoni_download_begin(PedoniModel* model, float* pos_xy, uint32_t* destination, uint32_t cap);
 int pedoni_download_end(PedoniModel* model, uint32_t* n_out);
@@ -290,6 +292,11 @@ const char* pedoni_slab_transport(const PedoniModel* model);
  * (strict handles; no memory for the second copy; maps that do not tile into 32768 x 32768 texels;
  * PEDONI_FIELD_TEXTURES=0). */
 int pedoni_field_textures(const PedoniModel* model);
+
+/* Bytes per pedestrian that pedoni_download_begin / _end move over PCIe: 8 (position) + 4 (destination), or
+ * + 1 when there are at most 256 potential maps — destinations then travel as bytes and pedoni_download_end
+ * widens them into the caller's uint32 array on the host (PEDONI_DOWNLOAD_PACK=0 turns this off). */
+int pedoni_download_wire_bytes(const PedoniModel* model);
 
 /* The halo capacity in effect (0 on a whole-domain handle). */
 int pedoni_halo_capacity(const PedoniModel* model, uint32_t* halo_capacity);

@@ -109,6 +109,7 @@ SIGNATURES = {
     "pedoni_slab_transport": (C.c_char_p, [C.c_void_p]),
     "pedoni_halo_capacity": (C.c_int, [C.c_void_p, c_u32_p]),
     "pedoni_field_textures": (C.c_int, [C.c_void_p]),
+    "pedoni_download_wire_bytes": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -129,14 +129,22 @@ struct PedoniModel {
 
     // pipelined list_pedestrians (pedoni_download_begin / _end)
     cudaStream_t dl_stream = nullptr;
-    cudaEvent_t ev_snap = nullptr, ev_dl_done = nullptr;
-    float2* d_snap_pos = nullptr;
-    uint32_t* d_snap_dest = nullptr;
-    uint32_t* d_snap_range = nullptr;  // owned [begin, end) copied on the main stream with the snapshot
-    uint32_t snap_cap = 0;
-    uint32_t* h_snap_range = nullptr;  // pinned: owned [begin, end) at snapshot time
-    bool dl_inflight = false;
-    uint32_t dl_cap = 0;
+    // Two downloads may be in flight (begin k, begin k+1, end k, ...): while the host widens the byte-sized
+    // destinations of tick k, tick k+1's copy keeps PCIe busy. pedoni_download_end completes the oldest.
+    struct DownloadSlot {
+        cudaEvent_t ev_snap = nullptr, ev_done = nullptr;
+        float2* d_pos = nullptr;
+        uint32_t* d_dest = nullptr;   // destinations as stored, or
+        uint8_t* d_dest8 = nullptr;   // one byte each when there are at most 256 potential maps: packed on the
+        uint8_t* h_dest8 = nullptr;   // device, staged in pinned memory, widened into the caller's array by _end
+        uint32_t* d_range = nullptr;  // owned [begin, end) copied on the main stream with the snapshot
+        uint32_t* h_range = nullptr;  // pinned
+        uint32_t cap = 0;             // elements of the snapshot buffers
+        uint32_t* user_dest = nullptr;
+        uint32_t user_cap = 0;
+        bool inflight = false;
+    } dl[2];
+    uint32_t dl_head = 0, dl_count = 0;  // oldest slot in flight, number in flight
 
     bool profiling = false;
     std::vector<TimedLaunch> timed;
@@ -603,6 +611,23 @@ __global__ void footprint_check_kernel(FieldView f, uint32_t* mismatch) {
     if (!same) atomicOr(mismatch, 1u);
 }
 
+// ---- pipelined download: destinations as bytes --------------------------------------------------------
+bool download_packs_destinations(const PedoniModel* m) {
+    const char* env = std::getenv("PEDONI_DOWNLOAD_PACK");
+    return m->field.n_maps <= 256 && !(env && env[0] == '0');  // live pedestrians have destination < n_maps (sort_key)
+}
+
+// four destinations per thread -> one 32-bit store of four bytes
+__global__ void __launch_bounds__(256) pack_dest_kernel(const uint32_t* __restrict__ dest, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x, i = 4 * q;
+    if (i >= n) return;
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i + k < n) w |= (dest[i + k] & 0xFFu) << (8 * k);
+    out[q] = w;
+}
+
 void release_field_textures(PedoniModel* m) {
     if (m->field.atlas) cudaDestroyTextureObject(m->field.atlas);
     if (m->field_atlas) cudaFreeArray(m->field_atlas);
@@ -895,12 +920,16 @@ void pedoni_destroy(PedoniModel* m) {
         cudaStreamSynchronize(m->dl_stream);
         cudaStreamDestroy(m->dl_stream);
     }
-    for (cudaEvent_t e : {m->ev_snap, m->ev_dl_done})
-        if (e) cudaEventDestroy(e);
-    cudaFree(m->d_snap_pos);
-    cudaFree(m->d_snap_dest);
-    cudaFree(m->d_snap_range);
-    if (m->h_snap_range) cudaFreeHost(m->h_snap_range);
+    for (auto& d : m->dl) {
+        for (cudaEvent_t e : {d.ev_snap, d.ev_done})
+            if (e) cudaEventDestroy(e);
+        cudaFree(d.d_pos);
+        cudaFree(d.d_dest);
+        cudaFree(d.d_dest8);
+        cudaFree(d.d_range);
+        if (d.h_dest8) cudaFreeHost(d.h_dest8);
+        if (d.h_range) cudaFreeHost(d.h_range);
+    }
     if (m->edge_stream) cudaStreamDestroy(m->edge_stream);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -1268,68 +1297,95 @@ int pedoni_download(PedoniModel* m, float* pos_xy, uint32_t* dest, float* vel_xy
 
 // Pipelined list_pedestrians: snapshot the owned (pos, destination) columns on the device (one D2D pass
 // behind the work already enqueued), then copy the snapshot to the caller's buffers on a separate
-// stream. The model may keep stepping meanwhile; pedoni_download_end waits for the copy.
+// stream. The model may keep stepping meanwhile; pedoni_download_end waits for the oldest copy in flight.
 int pedoni_download_begin(PedoniModel* m, float* pos_xy, uint32_t* dest, uint32_t cap) {
     if (!m || !pos_xy || !dest) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
-    if (m->dl_inflight) return fail(m, PEDONI_ERR_STATE, "a pipelined download is already in flight");
+    if (m->dl_count == 2) return fail(m, PEDONI_ERR_STATE, "two pipelined downloads are already in flight");
     if (m->app_n > 0) return fail(m, PEDONI_ERR_STATE, "pedoni_download_begin with un-rebuilt spawns");
-    if (!m->dl_stream) {
-        CUDA_TRY(m, cudaStreamCreateWithFlags(&m->dl_stream, cudaStreamNonBlocking));
-        CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_snap, cudaEventDisableTiming));
-        CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_dl_done, cudaEventDisableTiming));
-        CUDA_TRY(m, cudaHostAlloc(&m->h_snap_range, 2 * sizeof(uint32_t), cudaHostAllocDefault));
-        CUDA_TRY(m, cudaMalloc(&m->d_snap_range, 2 * sizeof(uint32_t)));
+    if (!m->dl_stream) CUDA_TRY(m, cudaStreamCreateWithFlags(&m->dl_stream, cudaStreamNonBlocking));
+    PedoniModel::DownloadSlot& d = m->dl[(m->dl_head + m->dl_count) & 1];
+    if (!d.ev_snap) {
+        CUDA_TRY(m, cudaEventCreateWithFlags(&d.ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(m, cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
+        CUDA_TRY(m, cudaHostAlloc(&d.h_range, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        CUDA_TRY(m, cudaMalloc(&d.d_range, 2 * sizeof(uint32_t)));
     }
     const uint32_t upper = m->owned_upper;  // host bound of the owned population; the exact count follows
-    if (upper > m->snap_cap) {
-        CUDA_TRY(m, cudaStreamSynchronize(m->dl_stream));
-        cudaFree(m->d_snap_pos);
-        cudaFree(m->d_snap_dest);
-        m->d_snap_pos = nullptr;
-        m->d_snap_dest = nullptr;
+    if (upper > d.cap) {  // the slot is free: its previous copy finished before pedoni_download_end returned
+        cudaFree(d.d_pos);
+        cudaFree(d.d_dest);
+        cudaFree(d.d_dest8);
+        if (d.h_dest8) cudaFreeHost(d.h_dest8);
+        d.d_pos = nullptr, d.d_dest = nullptr, d.d_dest8 = nullptr, d.h_dest8 = nullptr, d.cap = 0;
         const uint32_t ncap = std::max<uint32_t>(upper + upper / 8, 1024);
-        CUDA_TRY(m, cudaMalloc(&m->d_snap_pos, sizeof(float2) * (size_t)ncap));
-        CUDA_TRY(m, cudaMalloc(&m->d_snap_dest, sizeof(uint32_t) * (size_t)ncap));
-        m->snap_cap = ncap;
+        CUDA_TRY(m, cudaMalloc(&d.d_pos, sizeof(float2) * (size_t)ncap));
+        if (download_packs_destinations(m)) {
+            CUDA_TRY(m, cudaMalloc(&d.d_dest8, (size_t)ncap + 4));
+            CUDA_TRY(m, cudaHostAlloc(&d.h_dest8, (size_t)ncap + 4, cudaHostAllocDefault));
+        } else {
+            CUDA_TRY(m, cudaMalloc(&d.d_dest, sizeof(uint32_t) * (size_t)ncap));
+        }
+        d.cap = ncap;
     }
     const AgentArrays& a = m->buf[m->cur];
     const uint32_t take = std::min(upper, cap);
-    // the previous copy out of the snapshot buffers finished before pedoni_download_end returned
     if (upper) {
-        CUDA_TRY(m, cudaMemcpyAsync(m->d_snap_pos, a.pos + m->array_offset, sizeof(float2) * (size_t)upper,
+        CUDA_TRY(m, cudaMemcpyAsync(d.d_pos, a.pos + m->array_offset, sizeof(float2) * (size_t)upper,
                                     cudaMemcpyDeviceToDevice, m->stream));
-        CUDA_TRY(m, cudaMemcpyAsync(m->d_snap_dest, a.dest + m->array_offset, sizeof(uint32_t) * (size_t)upper,
-                                    cudaMemcpyDeviceToDevice, m->stream));
+        if (d.d_dest8)
+            pack_dest_kernel<<<div_up(div_up(upper, 4), 256), 256, 0, m->stream>>>(a.dest + m->array_offset, upper,
+                                                                                   reinterpret_cast<uint32_t*>(d.d_dest8));
+        else
+            CUDA_TRY(m, cudaMemcpyAsync(d.d_dest, a.dest + m->array_offset, sizeof(uint32_t) * (size_t)upper,
+                                        cudaMemcpyDeviceToDevice, m->stream));
     }
-    CUDA_TRY(m, cudaMemcpyAsync(m->d_snap_range, m->range(kRangeOwned), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+    CUDA_TRY(m, cudaMemcpyAsync(d.d_range, m->range(kRangeOwned), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
                                 m->stream));  // the next rebuild rewrites d_ranges: freeze the count with the data
-    CUDA_TRY(m, cudaEventRecord(m->ev_snap, m->stream));
-    CUDA_TRY(m, cudaStreamWaitEvent(m->dl_stream, m->ev_snap, 0));
-    CUDA_TRY(m, cudaMemcpyAsync(m->h_snap_range, m->d_snap_range, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                m->dl_stream));
+    CUDA_TRY(m, cudaEventRecord(d.ev_snap, m->stream));
+    CUDA_TRY(m, cudaStreamWaitEvent(m->dl_stream, d.ev_snap, 0));
+    CUDA_TRY(m, cudaMemcpyAsync(d.h_range, d.d_range, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->dl_stream));
     if (take) {
-        CUDA_TRY(m, cudaMemcpyAsync(pos_xy, m->d_snap_pos, sizeof(float2) * (size_t)take, cudaMemcpyDeviceToHost,
-                                    m->dl_stream));
-        CUDA_TRY(m, cudaMemcpyAsync(dest, m->d_snap_dest, sizeof(uint32_t) * (size_t)take, cudaMemcpyDeviceToHost,
-                                    m->dl_stream));
+        CUDA_TRY(m, cudaMemcpyAsync(pos_xy, d.d_pos, sizeof(float2) * (size_t)take, cudaMemcpyDeviceToHost, m->dl_stream));
+        if (d.d_dest8)
+            CUDA_TRY(m, cudaMemcpyAsync(d.h_dest8, d.d_dest8, (size_t)take, cudaMemcpyDeviceToHost, m->dl_stream));
+        else
+            CUDA_TRY(m, cudaMemcpyAsync(dest, d.d_dest, sizeof(uint32_t) * (size_t)take, cudaMemcpyDeviceToHost,
+                                        m->dl_stream));
     }
-    CUDA_TRY(m, cudaEventRecord(m->ev_dl_done, m->dl_stream));
-    m->dl_inflight = true;
-    m->dl_cap = cap;
+    CUDA_TRY(m, cudaEventRecord(d.ev_done, m->dl_stream));
+    d.user_dest = dest;
+    d.user_cap = cap;
+    d.inflight = true;
+    m->dl_count += 1;
     return PEDONI_OK;
 }
 
 int pedoni_download_end(PedoniModel* m, uint32_t* n_out) {
     if (!m) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
-    if (!m->dl_inflight) return fail(m, PEDONI_ERR_STATE, "no pipelined download in flight");
-    CUDA_TRY(m, cudaEventSynchronize(m->ev_dl_done));
-    m->dl_inflight = false;
-    const uint32_t n = m->h_snap_range[1] - m->h_snap_range[0];
+    if (m->dl_count == 0) return fail(m, PEDONI_ERR_STATE, "no pipelined download in flight");
+    PedoniModel::DownloadSlot& d = m->dl[m->dl_head];
+    CUDA_TRY(m, cudaEventSynchronize(d.ev_done));
+    d.inflight = false;
+    m->dl_head ^= 1;
+    m->dl_count -= 1;
+    const uint32_t n = d.h_range[1] - d.h_range[0];
     if (n_out) *n_out = n;
-    if (n > m->dl_cap) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", m->dl_cap, n);
+    if (n > d.user_cap) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", d.user_cap, n);
+    if (d.d_dest8) {  // widen the byte-sized destinations into the caller's array (a later download may be copying meanwhile)
+        const uint8_t* src = d.h_dest8;
+        uint32_t* dst = d.user_dest;
+        const long long count = n;
+#pragma omp parallel for schedule(static) if (count > (1 << 16))
+        for (long long i = 0; i < count; ++i) dst[i] = src[i];
+    }
     return PEDONI_OK;
+}
+
+int pedoni_download_wire_bytes(const PedoniModel* m) {
+    if (!m) return 0;
+    return static_cast<int>(sizeof(float2)) + (download_packs_destinations(m) ? 1 : 4);
 }
 
 int pedoni_observe(PedoniModel* m, float y0, float y1, uint32_t n_bins, PedoniObservables* out) {

@@ -162,13 +162,16 @@ class SocialForceModelCuda:
 
     def download_begin(self, pos: np.ndarray, dest: np.ndarray) -> None:
         """Pipelined `list_pedestrians`: snapshot on the device, copy to (pinned) `pos`/`dest` in the background."""
-        self._dl = (pos, dest)  # keep the buffers alive until download_end
         _capi.check(self._lib.pedoni_download_begin(self._h, _fp(pos), _up(dest), dest.shape[0]), self._h)
+        if not hasattr(self, "_dl"):
+            self._dl = []
+        self._dl.append((pos, dest))  # keep the buffers alive until download_end; up to two may be in flight
 
     def download_end(self):
+        """Completes the OLDEST pipelined download in flight."""
         n = C.c_uint32()
         _capi.check(self._lib.pedoni_download_end(self._h, C.byref(n)), self._h)
-        pos, dest = self._dl
+        pos, dest = self._dl.pop(0)
         return pos[: n.value], dest[: n.value]
 
     def observe(self, y_range=(0.0, 1.0), bins: int = 0) -> dict:
@@ -232,6 +235,10 @@ class SocialForceModelCuda:
 
     def slab_transport(self) -> str:
         return self._lib.pedoni_slab_transport(self._h).decode()
+
+    def download_wire_bytes(self) -> int:
+        """Bytes per pedestrian the pipelined download moves over PCIe (12, or 9 with byte-sized destinations)."""
+        return int(self._lib.pedoni_download_wire_bytes(self._h))
 
     def field_textures(self) -> bool:
         """True if the force kernel fetches the field maps with texture gathers (fast math only)."""

@@ -157,12 +157,16 @@ def test_empty_model_and_errors(corridor):
         helpers.make_pair(sc, field, options=SimulatorOptions(use_neighbor_grid=False))
 
 
-def test_pipelined_download_equals_blocking_download(corridor):
-    """pedoni_download_begin/_end: the snapshot is of the moment of the call, whatever is enqueued after it."""
+@pytest.mark.parametrize("pack", ["1", "0"])
+def test_pipelined_download_equals_blocking_download(corridor, monkeypatch, pack):
+    """pedoni_download_begin/_end: the snapshot is of the moment of the call, whatever is enqueued after it.
+    With at most 256 potential maps the destinations cross PCIe as bytes and are widened on the host."""
     import torch
+    monkeypatch.setenv("PEDONI_DOWNLOAD_PACK", pack)
     sc, field = corridor
     cu, _ = helpers.make_pair(sc, field)
-    pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=9, margin=4.0)
+    assert cu.download_wire_bytes() == (9 if pack == "1" else 12)
+    pos, dest, vel, v0 = helpers.random_crowd(3001, sc.field.size, seed=9, margin=4.0)
     cu.upload_state(pos, dest, vel, v0)
     cu.rebuild()
     h_pos = torch.empty((4000, 2), dtype=torch.float32).pin_memory().numpy()
@@ -225,3 +229,29 @@ def test_texture_gather_path_is_bit_identical_to_loads(corridor, monkeypatch):
     strict = SocialForceModelCuda(SimulatorOptions(), sc, field, math_mode=PEDONI_MATH_STRICT)
     assert not strict.field_textures()
     strict.close()
+
+
+def test_two_pipelined_downloads_in_flight(corridor):
+    """begin k, begin k+1, end k, end k+1: _end completes the oldest; a third begin is refused."""
+    import torch
+    from pedoni_b200 import PedoniError
+    sc, field = corridor
+    cu, _ = helpers.make_pair(sc, field)
+    pos, dest, vel, v0 = helpers.random_crowd(2500, sc.field.size, seed=12, margin=4.0)
+    cu.upload_state(pos, dest, vel, v0)
+    cu.rebuild()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    bufs = [(pin((3000, 2), torch.float32), pin(3000, torch.int32).view(np.uint32)) for _ in range(3)]
+    want = []
+    for k in range(2):
+        cu.step()
+        cu.rebuild()
+        want.append(cu.download(vel=False, v0=False)[:2])
+        cu.download_begin(*bufs[k])
+    with pytest.raises(PedoniError):
+        cu.download_begin(*bufs[2])
+    for k in range(2):
+        got_pos, got_dest = cu.download_end()
+        np.testing.assert_array_equal(bits(got_pos), bits(want[k][0]))
+        np.testing.assert_array_equal(got_dest, want[k][1])
+    cu.close()
