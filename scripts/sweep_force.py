@@ -25,10 +25,7 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
-SORT_VARIANTS = {"base": [], "b8": ["-DPEDONI_FORCE_MIN_BLOCKS=8"],
-                 "b10_t160_l24": ["-DPEDONI_FORCE_MIN_BLOCKS=10", "-DPEDONI_TILE_ENTRIES=160", "-DPEDONI_LIST_DEPTH=24"],
-                 "b7": ["-DPEDONI_FORCE_MIN_BLOCKS=7"], "unroll1": ["-DPEDONI_FORCE_UNROLL=1"], "unroll3": ["-DPEDONI_FORCE_UNROLL=3"],
-                 "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"]}
+SORT_VARIANTS = {"base": [], "scan12": ["-DPEDONI_SCAN_ITEMS=12"], "scan20": ["-DPEDONI_SCAN_ITEMS=20"], "scan24": ["-DPEDONI_SCAN_ITEMS=24"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
 OUT = ROOT / "build" / "variants"
