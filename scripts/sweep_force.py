@@ -25,7 +25,11 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
-SORT_VARIANTS = {"base": [], "scan12": ["-DPEDONI_SCAN_ITEMS=12"], "scan20": ["-DPEDONI_SCAN_ITEMS=20"], "scan24": ["-DPEDONI_SCAN_ITEMS=24"]}
+SORT_VARIANTS = {"base": [], "scan8": ["-DPEDONI_SCAN_ITEMS=8"], "scan32": ["-DPEDONI_SCAN_ITEMS=32"],
+                 "scatter4": ["-DPEDONI_SCATTER_ITEMS=4"], "gather2": ["-DPEDONI_GATHER_ITEMS=2"],
+                 "no_bulk": ["-DPEDONI_BULK_STAGE=0"],
+                 "t64_b18_t144_l24": ["-DPEDONI_FORCE_THREADS=64", "-DPEDONI_FORCE_MIN_BLOCKS=18", "-DPEDONI_TILE_ENTRIES=144",
+                                      "-DPEDONI_LIST_DEPTH=24"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
 OUT = ROOT / "build" / "variants"
