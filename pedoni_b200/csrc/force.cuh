@@ -17,11 +17,13 @@
 //      union per row offset is ONE contiguous index window [first lane's start, last lane's end)
 //      — also across a row end, because consecutive rows are adjacent in the sorted arrays. The bounds
 //      travel by warp shuffle.
-//   2. the three windows (position and velocity) are staged in the warp's slice of shared memory with
-//      cp.async (LDGSTS: no registers, no waiting) — ~4 coalesced 8-byte copies per agent instead of
-//      ~36 gathers — while the lanes issue and evaluate the steering / wall field samples.
-//   3. SCAN: each lane walks its candidates in the tile (one LDS.64 and the 2 m cut-off test, branch
-//      free) and appends the in-range ones to a private list in shared memory, in index order.
+//   2. the three windows (position and velocity) are staged in the warp's slice of shared memory by six
+//      bulk copies (cp.async.bulk / TMA, completion on a per-warp mbarrier: no registers, no LSU work, no
+//      waiting) instead of ~36 gathers per agent, while the lanes fetch and evaluate the steering / wall
+//      field samples — 4x4 texel footprints, four texture gathers each in fast math.
+//   3. SCAN: each lane walks its candidates in the tile, two per iteration (LDS.64 and the 2 m cut-off
+//      test, branch free, PTX) and appends the in-range ones to a private list in shared memory, in index
+//      order.
 //   4. FORCE: each lane evaluates the Helbing-Molnar term for its list, in the same order as the
 //      reference sums it. Splitting scan from force keeps the expensive body converged: a warp runs
 //      max-over-lanes(in-range) ~ 18 heavy iterations instead of sum-over-rows max-over-lanes
@@ -38,7 +40,7 @@ namespace pedoni {
 constexpr float kCosPhi = -0.17364817766693036f;  // sfm.rs:16
 constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0.y, b.x, b.y, |b|^2), w, h, pad
 
-// Tunables (overridable at build time for sweeps: scripts/sweep_force.sh).
+// Tunables (overridable at build time for sweeps: scripts/sweep_force.py).
 #ifndef PEDONI_FORCE_THREADS
 #define PEDONI_FORCE_THREADS 128
 #endif
