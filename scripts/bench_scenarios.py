@@ -26,6 +26,8 @@ from pedoni_b200.scenario import ObstacleConfig, Scenario, WaypointConfig, Field
 from pedoni_b200.simulator import Simulator  # noqa: E402
 
 QUICK = "--quick" in sys.argv
+MILLION_ONLY = "--million-only" in sys.argv  # skip the shipped scenarios
+NO_CPU = "--no-cpu" in sys.argv              # skip the CPU oracle legs (kernel A/B runs)
 
 
 def scaled(sc: Scenario, k: float) -> Scenario:
@@ -96,6 +98,8 @@ def row_million(name, k, dests, box_of):
     gpu, ms = time_cuda(model, 20)
     p, d, v, s = model.download()
     model.close()
+    if NO_CPU:
+        return f"{name} x{k:g} ({sc.field.size[0]:.0f} m x {sc.field.size[1]:.0f} m, field build {t_field:.0f} s)", n_live, gpu, ms, float("nan")
     obs = np.array([[*o.line[0], *o.line[1], o.width] for o in sc.obstacles], np.float32).reshape(-1, 5)
     om = oracle.OracleModel(sc.field.size, opts.neighbor_grid_unit, field.unit, field.distance_map, field.potential_maps,
                             obstacles=obs)
@@ -108,8 +112,8 @@ def row_million(name, k, dests, box_of):
 def main():
     oracle.lib().oracle_set_threads(__import__("os").cpu_count() or 1)
     rows = []
-    for name, warm, ticks in [("default", 600, 200), ("narrow-gap", 50, 100), ("bottleneck", 600, 100),
-                              ("evacuation", 30, 100), ("lanes", 600, 200), ("random", 600, 100)]:
+    for name, warm, ticks in [] if MILLION_ONLY else [("default", 600, 200), ("narrow-gap", 50, 100), ("bottleneck", 600, 100),
+                                                     ("evacuation", 30, 100), ("lanes", 600, 200), ("random", 600, 100)]:
         rows.append(row_shipped(name, warm // (4 if QUICK else 1), ticks))
         print("done", rows[-1][0], file=sys.stderr)
     rows.append(row_million("lanes", 46.0, [0, 1], lambda sc: (0.09 * sc.field.size[0], 0.5, 0.91 * sc.field.size[0], 8.0 * 46 - 0.5)))
