@@ -294,8 +294,10 @@ const char* pedoni_slab_transport(const PedoniModel* model);
 int pedoni_field_textures(const PedoniModel* model);
 
 /* Bytes per pedestrian that pedoni_download_begin / _end move over PCIe: 8 (position) + 4 (destination), or
- * + 1 when there are at most 256 potential maps — destinations then travel as bytes and pedoni_download_end
- * widens them into the caller's uint32 array on the host (PEDONI_DOWNLOAD_PACK=0 turns this off). */
+ * + 1 on a whole-domain handle with at most 256 potential maps — destinations then travel as bytes and
+ * pedoni_download_end widens them into the caller's uint32 array on the host. Slab handles keep 4-byte
+ * destinations (each GPU has its own link; the shared host is the limit there). PEDONI_DOWNLOAD_PACK=0 / 1
+ * overrides. */
 int pedoni_download_wire_bytes(const PedoniModel* model);
 
 /* The halo capacity in effect (0 on a whole-domain handle). */

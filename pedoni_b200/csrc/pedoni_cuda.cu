@@ -613,8 +613,14 @@ __global__ void footprint_check_kernel(FieldView f, uint32_t* mismatch) {
 
 // ---- pipelined download: destinations as bytes --------------------------------------------------------
 bool download_packs_destinations(const PedoniModel* m) {
+    // Whole-domain handles only: there ONE PCIe link carries every pedestrian and the bytes on it bound the
+    // tick. With one process per slab each GPU has its own link and the shared host (memory bandwidth,
+    // cores) is the limit; widening on the host then costs more than the bytes save (measured at 2 GPUs:
+    // 7.5e9 -> 3.6e9 updates/s end to end). PEDONI_DOWNLOAD_PACK=0 / 1 overrides.
     const char* env = std::getenv("PEDONI_DOWNLOAD_PACK");
-    return m->field.n_maps <= 256 && !(env && env[0] == '0');  // live pedestrians have destination < n_maps (sort_key)
+    if (m->field.n_maps > 256) return false;  // live pedestrians have destination < n_maps (sort_key)
+    if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
+    return m->slab_count <= 1;
 }
 
 // four destinations per thread -> one 32-bit store of four bytes
