@@ -1383,7 +1383,7 @@ int pedoni_download_end(PedoniModel* m, uint32_t* n_out) {
         const uint8_t* src = d.h_dest8;
         uint32_t* dst = d.user_dest;
         const long long count = n;
-#pragma omp parallel for schedule(static) if (count > (1 << 16))
+#pragma omp parallel for simd schedule(static) if (count > (1 << 16))
         for (long long i = 0; i < count; ++i) dst[i] = src[i];
     }
     return PEDONI_OK;
