@@ -294,14 +294,25 @@ def run_ours(args):
             model.rebuild()                           # spawn_pedestrians, second half
             model.step()                              # update_states
 
+        # One GPU: the next tick is enqueued BEFORE the previous tick's download is finished on the host, so
+        # the GPU computes while the host waits for the copy and widens the destinations (PCIe stays
+        # saturated: 1.88 -> 1.61 ms per tick). One process per slab: the plain order is faster (measured at
+        # 2 GPUs: 1.31 vs 2.31 ms per tick — the ranks' rebuilds exchange ghost rows and want to stay in
+        # lockstep; a rank sitting in a long host-side wait right after enqueueing delays its neighbour).
+        eager = world == 1
+
         def e2e_tick(k):
             """Steady state of the pipeline: tick k has been enqueued. Start its list_pedestrians (device
-            snapshot + async D2H), enqueue tick k+1 right away so the GPU computes it while the host finishes
-            tick k-1 (waits for its copy, widens its destinations), then finish tick k-1."""
+            snapshot + async D2H), enqueue tick k+1 and finish tick k-1 on the host (wait for its copy, widen
+            its destinations) — in the order `eager` says."""
             model.download_begin(*bufs[k % 2])
             state["inflight"] += 1
-            compute(k + 1)
-            collect(keep=1)
+            if eager:
+                compute(k + 1)
+                collect(keep=1)
+            else:
+                collect(keep=1)
+                compute(k + 1)
 
         compute(0)
         for k in range(max(args.warmup, 1)):
