@@ -447,6 +447,9 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t arrivals) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_sa), "r"(arrivals) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
 }
+__device__ __forceinline__ void mbar_inval(uint32_t mbar_sa) {  // before the memory is used for anything else
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_sa) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar_sa, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(bytes) : "memory");
 }
@@ -616,6 +619,9 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     cp_async_wait_all();
 #endif
     __syncwarp();
+#if PEDONI_BULK_STAGE
+    if (lane == 0) mbar_inval(mbar_sa);  // one phase per warp; the segment-wall variant reuses this memory below
+#endif
 
     // ---- pair repulsion (sfm.rs:112-156)
     if (live) {
