@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin
               cell_count, l.keys + l.idx, l.ticket + l.idx);
 }
 
-// ---- scan: exclusive prefix over n_cells counters in ONE pass (chained scan with decoupled look-back) --
+// ---- scan: exclusive prefix over n_cells counters in ONE pass (chained scan over tile aggregates) -------
 // A tile = 1024 threads x 16 cells (10 M pedestrians = 5.1 M cells = 312 tiles). Tiles are handed out by an atomic ticket (so a tile only ever waits for
 // tiles whose CTAs are already running), publish their aggregate in a 64-bit status word tagged with the
 // tick (no reset between launches), and sum their predecessors' aggregates for the exclusive prefix. The
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_cells_kernel(uint32_t* __re
     const uint32_t excl = block_exclusive_scan(sum, &s_total);
 
     // Exclusive prefix of the tile: every predecessor's aggregate, fetched in ONE round of loads spread over
-    // the block (a 32-wide look-back chain cost ~10 dependent L2 round trips for the last tiles of the wave).
+    // the block (no chain of dependent round trips through earlier tiles' prefixes).
     // Predecessors hold smaller tickets, so their CTAs are running or done: the spin cannot deadlock.
     {
         volatile unsigned long long* status = tile_status;
