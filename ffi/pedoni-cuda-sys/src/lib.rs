@@ -40,6 +40,46 @@ pub struct PedoniConfig {
     pub halo_capacity: u32,
 }
 
+#[repr(C)]
+pub struct PedoniSpawnGroup {
+    pub p1_x: f32,
+    pub p1_y: f32,
+    pub p2_x: f32,
+    pub p2_y: f32,
+    pub destination: u32,
+    pub count: u32,
+}
+
+#[repr(C)]
+pub struct PedoniObservables {
+    pub count: u32,
+    pub mean_speed: f32,
+    pub per_destination: [u32; 16],
+    pub arrived: [u64; 16],
+    pub n_bins: u32,
+    pub bin_count: [u32; 64],
+    pub bin_mean_vx: [f32; 64],
+}
+
+#[repr(C)]
+pub struct PedoniKernelTimes {
+    pub key_ms: f64,
+    pub histogram_ms: f64,
+    pub scan_ms: f64,
+    pub scatter_ms: f64,
+    pub gather_ms: f64,
+    pub force_ms: f64,
+    pub comm_ms: f64,
+    pub key_launches: u64,
+    pub histogram_launches: u64,
+    pub scan_launches: u64,
+    pub scatter_launches: u64,
+    pub gather_launches: u64,
+    pub force_launches: u64,
+    pub comm_launches: u64,
+    pub force_agents: u64,
+}
+
 extern "C" {
     pub fn pedoni_abi_version() -> c_int;
     pub fn pedoni_create(config: *const PedoniConfig, out_model: *mut *mut PedoniModel) -> c_int;
@@ -56,4 +96,31 @@ extern "C" {
     pub fn pedoni_slab_rows(ny: i32, count: i32, rank: i32, row0: *mut i32, row1: *mut i32) -> c_int;
     pub fn pedoni_comm_unique_id(out_id128: *mut c_void) -> c_int;
     pub fn pedoni_comm_init(model: *mut PedoniModel, id128: *const c_void) -> c_int;
+    // everything below: not needed by the trait shim (ffi/sfm_cuda.rs), declared so that this block mirrors
+    // the whole header (tests/test_capi_symbols.py checks the names)
+    pub fn pedoni_spawn_groups(model: *mut PedoniModel, n_groups: u32, groups: *const PedoniSpawnGroup, seed: u64,
+                               counter: u64) -> c_int;
+    pub fn pedoni_count_published(model: *mut PedoniModel, count: *mut i32, rebuild_ordinal: *mut u32) -> c_int;
+    pub fn pedoni_download_begin(model: *mut PedoniModel, pos_xy: *mut f32, destination: *mut u32, cap: u32) -> c_int;
+    pub fn pedoni_download_end(model: *mut PedoniModel, n_out: *mut u32) -> c_int;
+    pub fn pedoni_download_wire_bytes(model: *const PedoniModel) -> c_int;
+    pub fn pedoni_observe(model: *mut PedoniModel, y0: f32, y1: f32, n_bins: u32, out: *mut PedoniObservables) -> c_int;
+    pub fn pedoni_upload_state(model: *mut PedoniModel, n: u32, pos_xy: *const f32, destination: *const u32,
+                               vel_xy: *const f32, desired_speed: *const f32) -> c_int;
+    pub fn pedoni_grid_shape(model: *const PedoniModel, ny: *mut i32, nx: *mut i32) -> c_int;
+    pub fn pedoni_cell_table(model: *mut PedoniModel, indices: *mut u32, cap: u32, n_out: *mut u32) -> c_int;
+    pub fn pedoni_field_shape(size_x: f32, size_y: f32, unit: f32, field_ny: *mut i32, field_nx: *mut i32) -> c_int;
+    pub fn pedoni_field_build(size_x: f32, size_y: f32, unit: f32, n_obstacles: i32, obstacles: *const f32,
+                              n_waypoints: i32, waypoints: *const f32, obstacle_exist: *mut u8,
+                              distance_map: *mut f32, potential_maps: *mut f32) -> c_int;
+    pub fn pedoni_field_textures(model: *const PedoniModel) -> c_int;
+    pub fn pedoni_profile_enable(model: *mut PedoniModel, enable: i32) -> c_int;
+    pub fn pedoni_profile_reset(model: *mut PedoniModel) -> c_int;
+    pub fn pedoni_profile_read(model: *mut PedoniModel, out: *mut PedoniKernelTimes) -> c_int;
+    pub fn pedoni_counters(model: *mut PedoniModel, kernel_launches: *mut u64, pedestrian_updates: *mut u64) -> c_int;
+    pub fn pedoni_timer_begin(model: *mut PedoniModel) -> c_int;
+    pub fn pedoni_timer_end(model: *mut PedoniModel, elapsed_ms: *mut f32) -> c_int;
+    pub fn pedoni_slab_exchange_local(models: *const *mut PedoniModel, n: i32) -> c_int;
+    pub fn pedoni_slab_transport(model: *const PedoniModel) -> *const c_char;
+    pub fn pedoni_halo_capacity(model: *const PedoniModel, halo_capacity: *mut u32) -> c_int;
 }

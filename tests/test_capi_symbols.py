@@ -27,6 +27,18 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert lib.pedoni_abi_version() == _capi.PEDONI_ABI_VERSION
 
 
+def test_rust_extern_block_declares_the_same_functions():
+    """ffi/pedoni-cuda-sys cannot be compiled here (no Rust toolchain); at least its extern block names
+    exactly the functions of the header, and its PedoniConfig lists the header's fields in order."""
+    root = HEADER.parent.parent
+    rs = (root / "ffi" / "pedoni-cuda-sys" / "src" / "lib.rs").read_text()
+    assert sorted(set(re.findall(r"pub fn (pedoni_[a-z_0-9]+)\s*\(", rs))) == declared_symbols()
+    header = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    c_fields = re.findall(r"\b([a-z_0-9]+)\s*;", re.search(r"typedef struct PedoniConfig \{(.*?)\} PedoniConfig;", header, re.S).group(1))
+    rs_fields = re.findall(r"pub ([a-z_0-9]+):", re.search(r"pub struct PedoniConfig \{(.*?)\n\}", rs, re.S).group(1))
+    assert rs_fields == c_fields
+
+
 def test_config_struct_layout_matches_the_header(tmp_path):
     """Compile the real header with gcc (as C: the boundary is a C ABI) and compare every field offset."""
     import subprocess
