@@ -1,10 +1,10 @@
 //! UNVERIFIED SOURCE (no Rust toolchain in the build image): raw bindings of include/pedoni_cuda.h,
-//! ABI version 2. Field order and types mirror the C header one to one; tests/test_capi_symbols.py
+//! ABI version 3. Field order and types mirror the C header one to one; tests/test_capi_symbols.py
 //! checks the same layout against the header for the ctypes mirror.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const PEDONI_ABI_VERSION: c_int = 2;
+pub const PEDONI_ABI_VERSION: c_int = 3;
 pub const PEDONI_OK: c_int = 0;
 pub const PEDONI_MATH_STRICT: i32 = 0;
 pub const PEDONI_MATH_FAST: i32 = 1;
@@ -78,6 +78,19 @@ pub struct PedoniKernelTimes {
     pub force_launches: u64,
     pub comm_launches: u64,
     pub force_agents: u64,
+    pub force_edge_ms: f64,
+    pub pack_ms: f64,
+    pub force_edge_launches: u64,
+    pub pack_launches: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PedoniLaunchRecord {
+    pub kind: i32,
+    pub stream: i32,
+    pub start_ms: f32,
+    pub stop_ms: f32,
 }
 
 extern "C" {
@@ -123,4 +136,7 @@ extern "C" {
     pub fn pedoni_slab_exchange_local(models: *const *mut PedoniModel, n: i32) -> c_int;
     pub fn pedoni_slab_transport(model: *const PedoniModel) -> *const c_char;
     pub fn pedoni_halo_capacity(model: *const PedoniModel, halo_capacity: *mut u32) -> c_int;
+    pub fn pedoni_profile_timeline(model: *mut PedoniModel, out: *mut PedoniLaunchRecord, cap: u32, n_out: *mut u32) -> c_int;
+    pub fn pedoni_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn pedoni_host_free(ptr: *mut c_void);
 }

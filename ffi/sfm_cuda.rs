@@ -2,6 +2,7 @@
 //! implementation, to live at pedoni-simulator/src/models/sfm_cuda.rs next to sfm.rs and sfm_gpu.rs.
 //! See INTEGRATION.md for the three one-line edits that wire it in (models/mod.rs, lib.rs, args.rs).
 use std::ffi::CStr;
+use std::sync::Mutex;
 
 use glam::Vec2;
 use pedoni_cuda_sys as sys;
@@ -9,8 +10,34 @@ use pedoni_cuda_sys as sys;
 use super::PedestrianModel;
 use crate::{field::Field, scenario::Scenario, SimulatorOptions};
 
+/// Page-locked staging for `list_pedestrians`: the device-to-host copy runs at the PCIe rate only into pinned
+/// memory (pageable `Vec`s are staged by the driver at about a third of it). Grown on demand, reused every tick.
+struct Staging {
+    pos: *mut f32,
+    dest: *mut u32,
+    cap: usize,
+}
+
+impl Staging {
+    fn ensure(&mut self, n: usize) {
+        if n <= self.cap {
+            return;
+        }
+        unsafe {
+            sys::pedoni_host_free(self.pos as *mut _);
+            sys::pedoni_host_free(self.dest as *mut _);
+            let cap = (n + n / 8).max(4096);
+            self.pos = sys::pedoni_host_alloc(cap * 8) as *mut f32;
+            self.dest = sys::pedoni_host_alloc(cap * 4) as *mut u32;
+            assert!(!self.pos.is_null() && !self.dest.is_null(), "pedoni_host_alloc failed");
+            self.cap = cap;
+        }
+    }
+}
+
 pub struct SocialForceModelCuda {
     handle: *mut sys::PedoniModel,
+    staging: Mutex<Staging>, // list_pedestrians takes &self (models/mod.rs:23)
 }
 
 // The handle is moved to the simulation thread (main.rs:79-97) and used from one thread at a time.
@@ -66,7 +93,7 @@ impl PedestrianModel for SocialForceModelCuda {
             let msg = unsafe { CStr::from_ptr(sys::pedoni_last_error(std::ptr::null())) };
             panic!("pedoni_create failed ({rc}): {}", msg.to_string_lossy());
         }
-        SocialForceModelCuda { handle }
+        SocialForceModelCuda { handle, staging: Mutex::new(Staging { pos: std::ptr::null_mut(), dest: std::ptr::null_mut(), cap: 0 }) }
     }
 
     fn spawn_pedestrians(&mut self, _field: &Field, spawned: Vec<super::Pedestrian>) {
@@ -85,12 +112,16 @@ impl PedestrianModel for SocialForceModelCuda {
 
     fn list_pedestrians(&self) -> Vec<super::Pedestrian> {
         let n = self.get_pedestrian_count() as usize;
-        let (mut pos, mut dest) = (vec![0f32; 2 * n], vec![0u32; n]);
+        let mut st = self.staging.lock().unwrap();
+        st.ensure(n);
         let mut n_out = 0u32;
         self.check(unsafe {
-            sys::pedoni_download(self.handle, pos.as_mut_ptr(), dest.as_mut_ptr(), std::ptr::null_mut(),
-                                 std::ptr::null_mut(), n as u32, &mut n_out)
+            sys::pedoni_download(self.handle, st.pos, st.dest, std::ptr::null_mut(), std::ptr::null_mut(), n as u32,
+                                 &mut n_out)
         });
+        let (pos, dest) = unsafe {
+            (std::slice::from_raw_parts(st.pos, 2 * n_out as usize), std::slice::from_raw_parts(st.dest, n_out as usize))
+        };
         (0..n_out as usize)
             .map(|i| super::Pedestrian { pos: Vec2::new(pos[2 * i], pos[2 * i + 1]), destination: dest[i] as usize })
             .collect()
@@ -103,6 +134,11 @@ impl PedestrianModel for SocialForceModelCuda {
 
 impl Drop for SocialForceModelCuda {
     fn drop(&mut self) {
-        unsafe { sys::pedoni_destroy(self.handle) }
+        let st = self.staging.lock().unwrap();
+        unsafe {
+            sys::pedoni_host_free(st.pos as *mut _);
+            sys::pedoni_host_free(st.dest as *mut _);
+            sys::pedoni_destroy(self.handle)
+        }
     }
 }

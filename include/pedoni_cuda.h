@@ -27,13 +27,14 @@
 #ifndef PEDONI_CUDA_H
 #define PEDONI_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define PEDONI_ABI_VERSION 2
+#define PEDONI_ABI_VERSION 3
 
 typedef struct PedoniModel PedoniModel;
 
@@ -111,6 +112,9 @@ const char* pedoni_last_error(const PedoniModel* model);
  * velocity. desired_speed is an INPUT (the reference draws it from an unseeded global RNG,
  * sfm.rs:54; the caller draws it so device code stays RNG-free). n may be 0.
  * On a slab handle every rank is given the same list; a rank keeps the agents whose cell row it owns.
+ * The arrays may be pageable or pinned, and all of them may be reused as soon as the call returns: they
+ * are copied into a pinned staging ring of the handle on the host and travel from there, so the call
+ * never waits for the device (it only blocks if more than 4 MiB of spawns are still in flight).
  */
 int pedoni_spawn(PedoniModel* model, uint32_t n, const float* pos_xy, const uint32_t* destination,
                  const float* desired_speed);
@@ -147,7 +151,11 @@ int pedoni_rebuild(PedoniModel* model);
 /* PedestrianModel::update_states (sfm.rs:91-255): forces + integration, dt = 0.1 s. */
 int pedoni_step(PedoniModel* model);
 
-/* PedestrianModel::get_pedestrian_count (sfm.rs:267-269). Blocks. Negative = PedoniStatus. */
+/* PedestrianModel::get_pedestrian_count (sfm.rs:267-269). Blocks. Negative = PedoniStatus.
+ * A whole-domain handle counts the pedestrians appended since the last rebuild too (the reference's
+ * PedestrianVec holds them). A slab handle does not, here and in pedoni_download: spawn lists are
+ * replicated to every slab of a group and only the rebuild decides which slab keeps a newcomer, so
+ * between pedoni_spawn and pedoni_rebuild a slab reports its rebuilt pedestrians only. */
 int32_t pedoni_count(PedoniModel* model);
 
 /* The same without blocking: the population of the owned rows as of the most
@@ -237,7 +245,24 @@ typedef struct PedoniKernelTimes {
     uint64_t key_launches, histogram_launches, scan_launches, scatter_launches, gather_launches,
         force_launches, comm_launches;
     uint64_t force_agents; /* agents processed by the timed force launches */
+    /* slab handles (ABI 3): force = the interior launch on the main stream; force_edge = the launches on the rows
+     * next to a slab boundary (edge stream, concurrent with the interior launch); pack = halo_pack_kernel (main
+     * stream; with the peer-memory transport it also stores the strips into the neighbours). */
+    double force_edge_ms, pack_ms;
+    uint64_t force_edge_launches, pack_launches;
 } PedoniKernelTimes;
+
+/* One timed launch (profiling on): kind = 0 key, 2 scan, 3 scatter, 4 gather, 5 force (interior), 6 exchange +
+ * unpack, 7 force (edge rows), 8 pack; stream = 0 main, 1 edge; start / stop in milliseconds after the
+ * last pedoni_timer_begin (CUDA events; both streams share the origin). */
+typedef struct PedoniLaunchRecord {
+    int32_t kind;
+    int32_t stream;
+    float start_ms, stop_ms;
+} PedoniLaunchRecord;
+/* The launches timed since the last pedoni_timer_begin / pedoni_profile_reset (at most 4096): a two-stream
+ * timeline of the tick, for finding the critical path of a slab handle. *n_out = records available. Blocks. */
+int pedoni_profile_timeline(PedoniModel* model, PedoniLaunchRecord* out, uint32_t cap, uint32_t* n_out);
 
 int pedoni_profile_enable(PedoniModel* model, int32_t enable); /* per-kernel events; off by default */
 int pedoni_profile_reset(PedoniModel* model);
@@ -299,6 +324,11 @@ int pedoni_field_textures(const PedoniModel* model);
  * destinations (each GPU has its own link; the shared host is the limit there). PEDONI_DOWNLOAD_PACK=0 / 1
  * overrides. */
 int pedoni_download_wire_bytes(const PedoniModel* model);
+
+/* Page-locked host memory for the caller's download buffers (pedoni_download / pedoni_download_begin copy at the
+ * PCIe rate only into pinned memory; a Rust or C host need not link the CUDA runtime for it). NULL on failure. */
+void* pedoni_host_alloc(size_t bytes);
+void pedoni_host_free(void* ptr);
 
 /* The halo capacity in effect (0 on a whole-domain handle). */
 int pedoni_halo_capacity(const PedoniModel* model, uint32_t* halo_capacity);

@@ -12,7 +12,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libpedoni_cuda.so"
 
-PEDONI_ABI_VERSION = 2
+PEDONI_ABI_VERSION = 3
 PEDONI_OK = 0
 PEDONI_ERR_INVALID = -1
 PEDONI_ERR_CUDA = -2
@@ -70,7 +70,13 @@ class PedoniKernelTimes(C.Structure):
                 ("key_ms", "histogram_ms", "scan_ms", "scatter_ms", "gather_ms", "force_ms", "comm_ms")] + \
                [(n, C.c_uint64) for n in
                 ("key_launches", "histogram_launches", "scan_launches", "scatter_launches", "gather_launches",
-                 "force_launches", "comm_launches", "force_agents")]
+                 "force_launches", "comm_launches", "force_agents")] + \
+               [("force_edge_ms", C.c_double), ("pack_ms", C.c_double), ("force_edge_launches", C.c_uint64),
+                ("pack_launches", C.c_uint64)]
+
+
+class PedoniLaunchRecord(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("stream", C.c_int32), ("start_ms", C.c_float), ("stop_ms", C.c_float)]
 
 
 # name -> (restype, argtypes): every symbol include/pedoni_cuda.h declares.
@@ -110,6 +116,9 @@ SIGNATURES = {
     "pedoni_halo_capacity": (C.c_int, [C.c_void_p, c_u32_p]),
     "pedoni_field_textures": (C.c_int, [C.c_void_p]),
     "pedoni_download_wire_bytes": (C.c_int, [C.c_void_p]),
+    "pedoni_profile_timeline": (C.c_int, [C.c_void_p, C.POINTER(PedoniLaunchRecord), C.c_uint32, c_u32_p]),
+    "pedoni_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "pedoni_host_free": (None, [C.c_void_p]),
 }
 
 _lib = None

@@ -35,10 +35,11 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum KernelKind { kKey = 0, kHistogram, kScan, kScatter, kGather, kForce, kComm, kNumKinds };
+enum KernelKind { kKey = 0, kHistogram, kScan, kScatter, kGather, kForce, kComm, kForceEdge, kPack, kNumKinds };
 
 struct TimedLaunch {
     int kind;
+    int stream_id;  // 0: main stream, 1: edge stream
     cudaEvent_t start, stop;
     uint64_t agents;
 };
@@ -99,6 +100,15 @@ struct PedoniModel {
     void* d_spawn_groups = nullptr;  // SpawnGroupDev table of pedoni_spawn_groups
     uint32_t spawn_groups_cap = 0;
     uint32_t app_cap = 0, app_n = 0;
+    // Spawn staging: the caller's arrays (pageable or pinned) are copied into a pinned ring slot on the host and
+    // travel from there, so pedoni_spawn never waits for the stream and never reads a borrowed buffer after it
+    // returns. A slot is reused once the copies that read it have completed (event per slot).
+    static constexpr int kStageSlots = 4;
+    static constexpr size_t kStageBytes = 1u << 20;
+    unsigned char* h_stage[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_stage[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool stage_busy[kStageSlots] = {false, false, false, false};
+    int stage_next = 0;
 
     uint32_t* d_perm = nullptr;
     uint32_t aux_cap = 0;
@@ -148,6 +158,8 @@ struct PedoniModel {
 
     bool profiling = false;
     std::vector<TimedLaunch> timed;
+    std::vector<PedoniLaunchRecord> timeline;  // per-launch offsets since the last pedoni_timer_begin (profiling on)
+    bool timer_armed = false;
     std::vector<cudaEvent_t> event_pool;
     double acc_ms[kNumKinds] = {0};
     uint64_t acc_launches[kNumKinds] = {0};
@@ -322,6 +334,7 @@ struct ScopedTimer {
         : m(m_), s(stream), on(m_->profiling) {
         if (!on) return;
         t.kind = kind;
+        t.stream_id = (m->edge_stream && stream == m->edge_stream) ? 1 : 0;
         t.agents = agents;
         t.start = take_event(m);
         t.stop = take_event(m);
@@ -344,6 +357,14 @@ int drain_timed(PedoniModel* m) {
         m->acc_ms[t.kind] += ms;
         m->acc_launches[t.kind] += 1;
         if (t.kind == kForce) m->acc_force_agents += t.agents;
+        if (m->timer_armed && m->timeline.size() < 4096) {  // offsets from the last pedoni_timer_begin
+            float t0 = 0.f, t1 = 0.f;
+            if (cudaEventElapsedTime(&t0, m->timer_start, t.start) == cudaSuccess &&
+                cudaEventElapsedTime(&t1, m->timer_start, t.stop) == cudaSuccess)
+                m->timeline.push_back(PedoniLaunchRecord{t.kind, t.stream_id, t0, t1});
+            else
+                (void)cudaGetLastError();
+        }
         m->event_pool.push_back(t.start);
         m->event_pool.push_back(t.stop);
     }
@@ -432,7 +453,7 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     p.obstacle_edges = m->d_edges;
     p.n_obstacles = m->use_distance_map ? 0 : m->n_obstacles;
     const size_t smem = kForceSmemBytes;  // tile + neighbour lists; the segment-wall variant reuses the tile
-    ScopedTimer t(m, kForce, s, count_upper);
+    ScopedTimer t(m, (m->edge_stream && s == m->edge_stream) ? kForceEdge : kForce, s, count_upper);
     if (m->math_mode == PEDONI_MATH_STRICT) {
         if (m->use_distance_map)
             launch_force_t<Math::Strict, true, false>(m, p, blocks, smem, s);
@@ -458,24 +479,39 @@ int check_device_error(PedoniModel* m) {
     CUDA_TRY(m, cudaStreamSynchronize(m->stream));
     if (bits == 0) return PEDONI_OK;
     CUDA_TRY(m, cudaMemsetAsync(m->d_error, 0, sizeof(uint32_t), m->stream));
-    if (bits & kErrBadDestination)
-        return fail(m, PEDONI_ERR_INVALID,
-                    "device flagged an invalid agent (destination >= n_potential_maps); the reference would panic "
-                    "with an index-out-of-bounds at field.rs:237");
-    if (bits & kErrHaloOverflow)
-        return fail(m, PEDONI_ERR_CAPACITY,
-                    "two boundary rows of a slab hold more than halo_capacity = %u agents (or the ghost strip "
-                    "overran the arrays); raise PedoniConfig.halo_capacity", m->halo_cap);
+    // Every raised bit is reported; the return code is that of the most severe one.
+    std::string msg;
+    int code = PEDONI_OK;
+    auto add = [&](int c, const char* fmt, ...) {
+        char buf[400];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        if (!msg.empty()) msg += "; ";
+        msg += buf;
+        if (code == PEDONI_OK) code = c;
+    };
     if (bits & kErrStageTimeout)
-        return fail(m, PEDONI_ERR_CUDA, "force kernel: the bulk copies staging a warp's neighbour tile never completed");
+        add(PEDONI_ERR_CUDA, "force kernel: the bulk copies staging a warp's neighbour tile never completed");
     if (bits & kErrHaloTimeout)
-        return fail(m, PEDONI_ERR_COMM,
-                    "slab %d of %d waited 20 s for a neighbour's ghost strip (peer-memory transport): a rank died or "
-                    "the ranks do not call pedoni_rebuild in lockstep", m->slab_rank, m->slab_count);
-    return fail(m, PEDONI_ERR_STATE,
-                "a pedestrian crossed two or more neighbor-grid rows in one step; the slab decomposition "
-                "exchanges two ghost rows per tick and cannot follow it (speed > %.1f m/s)",
-                m->grid.unit / 0.1f);
+        add(PEDONI_ERR_COMM,
+            "slab %d of %d waited 20 s for a neighbour's ghost strip (peer-memory transport): a rank died or the "
+            "ranks do not call pedoni_rebuild in lockstep", m->slab_rank, m->slab_count);
+    if (bits & kErrHaloOverflow)
+        add(PEDONI_ERR_CAPACITY,
+            "two boundary rows of a slab hold more than halo_capacity = %u agents (or the ghost strip overran the "
+            "arrays); raise PedoniConfig.halo_capacity", m->halo_cap);
+    if (bits & kErrBadDestination)
+        add(PEDONI_ERR_INVALID,
+            "device flagged an invalid agent (destination >= n_potential_maps); the reference would panic with an "
+            "index-out-of-bounds at field.rs:237");
+    if (bits & kErrRowJump)
+        add(PEDONI_ERR_STATE,
+            "a pedestrian crossed two or more neighbor-grid rows in one step; the slab decomposition exchanges two "
+            "ghost rows per tick and cannot follow it (speed > %.1f m/s)", m->grid.unit / 0.1f);
+    if (code == PEDONI_OK) add(PEDONI_ERR_STATE, "unknown device error bits 0x%x", bits);
+    return fail(m, code, "%s", msg.c_str());
 }
 
 __global__ void reset_layout_kernel(uint32_t* ranges, uint32_t offset, unsigned long long* host_slot, uint32_t tick) {
@@ -552,21 +588,40 @@ int setup_peer_transport(PedoniModel* m) {
     int* d_ok = nullptr;
     cudaIpcMemHandle_t mine{}, from_below{}, from_above{};
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    CUDA_TRY(m, cudaMalloc(&d_handles, 3 * 64));
-    CUDA_TRY(m, cudaMalloc(&d_ok, sizeof(int)));
+    // every exit path frees the scratch buffers; a rank that ends up on NCCL closes what it had mapped
+    auto finish = [&](int rc) {
+        cudaFree(d_handles);
+        cudaFree(d_ok);
+        if (rc != PEDONI_OK || m->transport != PedoniModel::kTransportPeer) {
+            if (m->peer_arena_below) cudaIpcCloseMemHandle(m->peer_arena_below);
+            if (m->peer_arena_above) cudaIpcCloseMemHandle(m->peer_arena_above);
+            m->peer_arena_below = m->peer_arena_above = nullptr;
+            (void)cudaGetLastError();
+        }
+        return rc;
+    };
+#define PEER_TRY(expr)                                                                                           \
+    do {                                                                                                         \
+        cudaError_t err__ = (expr);                                                                              \
+        if (err__ != cudaSuccess)                                                                                \
+            return finish(fail(m, PEDONI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),    \
+                               __FILE__, __LINE__));                                                             \
+    } while (0)
+    PEER_TRY(cudaMalloc(&d_handles, 3 * 64));
+    PEER_TRY(cudaMalloc(&d_ok, sizeof(int)));
     if (ok && cudaIpcGetMemHandle(&mine, m->d_arena) != cudaSuccess) {
         ok = 0;
         (void)cudaGetLastError();
     }
-    CUDA_TRY(m, cudaMemcpyAsync(d_handles, &mine, 64, cudaMemcpyHostToDevice, m->edge_stream));
+    PEER_TRY(cudaMemcpyAsync(d_handles, &mine, 64, cudaMemcpyHostToDevice, m->edge_stream));
     std::string err;
     // my handle goes to both neighbours; theirs come back (same pattern as a ghost exchange)
     int rc = pedoni::slab_comm_exchange(m->comm, m->edge_stream, d_handles, d_handles + 64, d_handles, d_handles + 128, 64,
                                         m->has_below, m->has_above, &err);
-    if (rc != PEDONI_OK) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
-    CUDA_TRY(m, cudaMemcpyAsync(&from_below, d_handles + 64, 64, cudaMemcpyDeviceToHost, m->edge_stream));
-    CUDA_TRY(m, cudaMemcpyAsync(&from_above, d_handles + 128, 64, cudaMemcpyDeviceToHost, m->edge_stream));
-    CUDA_TRY(m, cudaStreamSynchronize(m->edge_stream));
+    if (rc != PEDONI_OK) return finish(fail(m, PEDONI_ERR_COMM, "%s", err.c_str()));
+    PEER_TRY(cudaMemcpyAsync(&from_below, d_handles + 64, 64, cudaMemcpyDeviceToHost, m->edge_stream));
+    PEER_TRY(cudaMemcpyAsync(&from_above, d_handles + 128, 64, cudaMemcpyDeviceToHost, m->edge_stream));
+    PEER_TRY(cudaStreamSynchronize(m->edge_stream));
     void* p = nullptr;
     if (ok && m->has_below) {
         if (cudaIpcOpenMemHandle(&p, from_below, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
@@ -581,15 +636,14 @@ int setup_peer_transport(PedoniModel* m) {
             ok = 0;
     }
     (void)cudaGetLastError();
-    CUDA_TRY(m, cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, m->edge_stream));
+    PEER_TRY(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, m->edge_stream));
     rc = pedoni::slab_comm_all_min(m->comm, m->edge_stream, d_ok, &err);
-    if (rc != PEDONI_OK) return fail(m, PEDONI_ERR_COMM, "%s", err.c_str());
-    CUDA_TRY(m, cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, m->edge_stream));
-    CUDA_TRY(m, cudaStreamSynchronize(m->edge_stream));
-    cudaFree(d_handles);
-    cudaFree(d_ok);
+    if (rc != PEDONI_OK) return finish(fail(m, PEDONI_ERR_COMM, "%s", err.c_str()));
+    PEER_TRY(cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, m->edge_stream));
+    PEER_TRY(cudaStreamSynchronize(m->edge_stream));
+#undef PEER_TRY
     m->transport = ok ? PedoniModel::kTransportPeer : PedoniModel::kTransportNccl;
-    return PEDONI_OK;
+    return finish(PEDONI_OK);
 }
 
 // ---- field maps as one texture atlas (fast math) -------------------------------------------------------
@@ -922,6 +976,10 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena, m->d_spawn_groups})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
+    for (int k = 0; k < PedoniModel::kStageSlots; ++k) {
+        if (m->ev_stage[k]) cudaEventDestroy(m->ev_stage[k]);
+        if (m->h_stage[k]) cudaFreeHost(m->h_stage[k]);
+    }
     if (m->dl_stream) {
         cudaStreamSynchronize(m->dl_stream);
         cudaStreamDestroy(m->dl_stream);
@@ -957,21 +1015,39 @@ static int append_agents(PedoniModel* m, uint32_t n, const float* pos_xy, const 
         return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
     int rc = ensure_app_capacity(m, m->app_n + n);
     if (rc != PEDONI_OK) return rc;
-    const uint32_t at = m->app_n;
-    CUDA_TRY(m, cudaMemcpyAsync(m->app.pos + at, pos_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(m, cudaMemcpyAsync(m->app.dest + at, dest, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(m, cudaMemcpyAsync(m->app.v0 + at, v0, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
-    if (vel_xy)
-        CUDA_TRY(m, cudaMemcpyAsync(m->app.vel + at, vel_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice,
-                                    m->stream));
-    else  // sfm.rs:53 velocity: Vec2::ZERO
-        CUDA_TRY(m, cudaMemsetAsync(m->app.vel + at, 0, sizeof(float2) * (size_t)n, m->stream));
-    // Pageable sources are staged before cudaMemcpyAsync returns; pinned sources are read
-    // asynchronously, and the caller's buffers are only borrowed for the call -> wait.
-    cudaPointerAttributes attr{};
-    if (cudaPointerGetAttributes(&attr, pos_xy) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered)
-        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
-    (void)cudaGetLastError();
+    // Through the pinned staging ring, chunk by chunk: one slot holds [pos | vel | v0 | dest] of up to
+    // `per_slot` pedestrians. The host copy into the slot ends before this call returns (the caller's arrays
+    // are borrowed for the call only, whatever kind of memory they are); the H2D copies read the slot.
+    const size_t per_agent = sizeof(float2) * (vel_xy ? 2 : 1) + sizeof(float) + sizeof(uint32_t);
+    const uint32_t per_slot = static_cast<uint32_t>((PedoniModel::kStageBytes - 64) / per_agent) & ~3u;  // 64: padding between the arrays
+    for (uint32_t done = 0; done < n;) {
+        const uint32_t k = std::min(per_slot, n - done), at = m->app_n + done;
+        const int slot = m->stage_next;
+        m->stage_next = (slot + 1) % PedoniModel::kStageSlots;
+        if (!m->h_stage[slot]) {
+            CUDA_TRY(m, cudaHostAlloc(&m->h_stage[slot], PedoniModel::kStageBytes, cudaHostAllocDefault));
+            CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_stage[slot], cudaEventDisableTiming));
+        }
+        if (m->stage_busy[slot]) CUDA_TRY(m, cudaEventSynchronize(m->ev_stage[slot]));  // copies issued 4 chunks ago
+        unsigned char* h = m->h_stage[slot];
+        size_t off = 0;
+        auto stage = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+            std::memcpy(h + off, src, bytes);
+            cudaError_t e = cudaMemcpyAsync(dst, h + off, bytes, cudaMemcpyHostToDevice, m->stream);
+            off += (bytes + 15) & ~static_cast<size_t>(15);
+            return e;
+        };
+        CUDA_TRY(m, stage(m->app.pos + at, pos_xy + 2 * (size_t)done, sizeof(float2) * (size_t)k));
+        if (vel_xy)
+            CUDA_TRY(m, stage(m->app.vel + at, vel_xy + 2 * (size_t)done, sizeof(float2) * (size_t)k));
+        else  // sfm.rs:53 velocity: Vec2::ZERO
+            CUDA_TRY(m, cudaMemsetAsync(m->app.vel + at, 0, sizeof(float2) * (size_t)k, m->stream));
+        CUDA_TRY(m, stage(m->app.v0 + at, v0 + done, sizeof(float) * (size_t)k));
+        CUDA_TRY(m, stage(m->app.dest + at, dest + done, sizeof(uint32_t) * (size_t)k));
+        CUDA_TRY(m, cudaEventRecord(m->ev_stage[slot], m->stream));
+        m->stage_busy[slot] = true;
+        done += k;
+    }
     m->app_n += n;
     m->table_valid = false;
     return PEDONI_OK;
@@ -1048,7 +1124,9 @@ static int rebuild_impl(PedoniModel* m) {
     const uint32_t total = resident + m->app_n;
     const uint64_t need = (uint64_t)m->array_offset + total + (m->has_above ? m->halo_cap : 0);
     if (need > 0xFFFFFFF0ull) return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
-    int rc = ensure_capacity(m, static_cast<uint32_t>(need), std::max<uint32_t>(total, 1));
+    // perm is indexed by cell_start[key] + ticket, and cell_start includes the array offset (the halo capacity on a
+    // slab with a neighbour below): size it like the arrays, not by the sort input alone.
+    int rc = ensure_capacity(m, static_cast<uint32_t>(need), std::max<uint32_t>(m->array_offset + total, 1));
     if (rc != PEDONI_OK) return rc;
     SortInput in = make_sort_input(m);
 
@@ -1120,10 +1198,13 @@ static int rebuild_impl(PedoniModel* m) {
                 sig.flag_up = m->flag_below(m->peer_arena_above);
             }
         }
-        halo_pack_kernel<<<grid, 256, 0, s>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell, m->own_end_cell,
-                                              m->grid.nx, m->halo_cap, down, up, m->has_below, m->has_above, m->tick,
-                                              m->d_error, sig);
-        m->launches += 1;
+        {
+            ScopedTimer t(m, kPack, s);
+            halo_pack_kernel<<<grid, 256, 0, s>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell, m->own_end_cell,
+                                                  m->grid.nx, m->halo_cap, down, up, m->has_below, m->has_above,
+                                                  m->tick, m->d_error, sig);
+            m->launches += 1;
+        }
         CUDA_TRY(m, cudaEventRecord(m->ev_packed, s));
         m->halo_pending = true;
         if (m->transport == PedoniModel::kTransportPeer)
@@ -1258,7 +1339,10 @@ int32_t pedoni_count(PedoniModel* m) {
     uint32_t b, e;
     int rc = sync_range(m, &b, &e);
     if (rc != PEDONI_OK) return rc;
-    return static_cast<int32_t>(e - b + m->app_n);
+    // Spawn lists are replicated to every slab of a group and only the rebuild decides which slab keeps a
+    // newcomer: a slab handle reports rebuilt pedestrians only (a whole-domain handle, like the reference's
+    // PedestrianVec, also counts the ones appended since the last rebuild).
+    return static_cast<int32_t>(e - b + (m->slab_count > 1 ? 0u : m->app_n));
 }
 
 // Non-blocking population: what the device last published (after the most recent COMPLETED rebuild).
@@ -1277,9 +1361,10 @@ int pedoni_download(PedoniModel* m, float* pos_xy, uint32_t* dest, float* vel_xy
     uint32_t b, e;
     int rc = sync_range(m, &b, &e);
     if (rc != PEDONI_OK) return rc;
-    const uint32_t n_cur = e - b, n = n_cur + m->app_n;
+    const uint32_t pending = m->slab_count > 1 ? 0u : m->app_n;  // see pedoni_count
+    const uint32_t n_cur = e - b, n = n_cur + pending;
     if (n_out) *n_out = n;
-    const uint32_t take_cur = std::min(n_cur, cap), take_app = std::min(m->app_n, cap - take_cur);
+    const uint32_t take_cur = std::min(n_cur, cap), take_app = std::min(pending, cap - take_cur);
     const AgentArrays& a = m->buf[m->cur];
     auto pull = [&](void* dst, const void* src_cur, const void* src_app, size_t elem) -> cudaError_t {
         if (!dst) return cudaSuccess;
@@ -1470,6 +1555,7 @@ int pedoni_profile_reset(PedoniModel* m) {
         m->acc_launches[k] = 0;
     }
     m->acc_force_agents = 0;
+    m->timeline.clear();
     return rc;
 }
 int pedoni_profile_read(PedoniModel* m, PedoniKernelTimes* out) {
@@ -1492,7 +1578,31 @@ int pedoni_profile_read(PedoniModel* m, PedoniKernelTimes* out) {
     out->force_launches = m->acc_launches[kForce];
     out->comm_launches = m->acc_launches[kComm];
     out->force_agents = m->acc_force_agents;
+    out->force_edge_ms = m->acc_ms[kForceEdge];
+    out->pack_ms = m->acc_ms[kPack];
+    out->force_edge_launches = m->acc_launches[kForceEdge];
+    out->pack_launches = m->acc_launches[kPack];
     return PEDONI_OK;
+}
+int pedoni_profile_timeline(PedoniModel* m, PedoniLaunchRecord* out, uint32_t cap, uint32_t* n_out) {
+    if (!m || !n_out) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    int rc = drain_timed(m);
+    if (rc != PEDONI_OK) return rc;
+    *n_out = static_cast<uint32_t>(m->timeline.size());
+    for (uint32_t k = 0; out && k < cap && k < m->timeline.size(); ++k) out[k] = m->timeline[k];
+    return PEDONI_OK;
+}
+void* pedoni_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pedoni_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 int pedoni_counters(PedoniModel* m, uint64_t* kernel_launches, uint64_t* pedestrian_updates) {
     if (!m) return PEDONI_ERR_INVALID;
@@ -1512,6 +1622,8 @@ int pedoni_timer_begin(PedoniModel* m) {
     if (!m) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
     CUDA_TRY(m, cudaEventRecord(m->timer_start, m->stream));
+    m->timer_armed = true;
+    m->timeline.clear();
     return PEDONI_OK;
 }
 int pedoni_timer_end(PedoniModel* m, float* ms) {

@@ -213,6 +213,18 @@ class SocialForceModelCuda:
         _capi.check(self._lib.pedoni_profile_read(self._h, C.byref(t)), self._h)
         return {name: getattr(t, name) for name, _ in t._fields_}
 
+    KIND_NAMES = {0: "key", 2: "scan", 3: "scatter", 4: "gather", 5: "force", 6: "exchange+unpack", 7: "force_edge",
+                  8: "pack"}
+
+    def profile_timeline(self) -> list:
+        """[(kernel, stream, start_ms, stop_ms)] of the launches timed since the last timer_begin (profiling on)."""
+        n = C.c_uint32()
+        _capi.check(self._lib.pedoni_profile_timeline(self._h, None, 0, C.byref(n)), self._h)
+        buf = (_capi.PedoniLaunchRecord * max(n.value, 1))()
+        _capi.check(self._lib.pedoni_profile_timeline(self._h, buf, n.value, C.byref(n)), self._h)
+        return [(self.KIND_NAMES.get(r.kind, str(r.kind)), "edge" if r.stream else "main", r.start_ms, r.stop_ms)
+                for r in buf[: n.value]]
+
     def counters(self):
         """(kernel launches, pedestrian-updates) since creation."""
         a, b = C.c_uint64(), C.c_uint64()

@@ -30,27 +30,7 @@ MILLION_ONLY = "--million-only" in sys.argv  # skip the shipped scenarios
 NO_CPU = "--no-cpu" in sys.argv              # skip the CPU oracle legs (kernel A/B runs)
 
 
-def scaled(sc: Scenario, k: float) -> Scenario:
-    s = lambda p: (p[0] * k, p[1] * k)  # noqa: E731
-    out = Scenario(field=FieldConfig(size=s(sc.field.size)))
-    out.waypoints = [WaypointConfig(line=(s(w.line[0]), s(w.line[1])), width=w.width * k) for w in sc.waypoints]
-    out.obstacles = [ObstacleConfig(line=(s(o.line[0]), s(o.line[1])), width=o.width * k) for o in sc.obstacles]
-    return out
-
-
-def seed_free_space(sc, field, n, dests, seed, box=None):
-    """n pedestrians uniformly where the distance map says > 0.6 m to the nearest obstacle."""
-    rng = np.random.default_rng(seed)
-    x0, y0, x1, y1 = box or (1.0, 1.0, sc.field.size[0] - 1.0, sc.field.size[1] - 1.0)
-    pos = np.empty((0, 2), np.float32)
-    while len(pos) < n:
-        p = np.stack([rng.uniform(x0, x1, n), rng.uniform(y0, y1, n)], 1).astype(np.float32)
-        ij = np.floor(p / field.unit).astype(int)
-        ok = field.distance_map[np.clip(ij[:, 1], 0, field.shape[0] - 1), np.clip(ij[:, 0], 0, field.shape[1] - 1)] > 0.6
-        pos = np.concatenate([pos, p[ok]])[:n]
-    dest = rng.choice(np.asarray(dests), n).astype(np.uint32)
-    v0 = np.clip(rng.normal(1.34, 0.26, n), 0.5, 2.2).astype(np.float32)
-    return pos, dest, v0
+from pedoni_b200.scaled import scaled_scenario as scaled, seed_free_space  # noqa: E402
 
 
 def time_cuda(model, ticks):

@@ -3,9 +3,12 @@
 
     python scripts/ncu_summary.py launches gpurun_out/launches.csv profiles/rNN_launches.md
     python scripts/ncu_summary.py kernel   gpurun_out/prof.ncu-rep  profiles/rNN_force.md [--id K]
+    python scripts/ncu_summary.py traffic  profiles/rNN_traffic.json --agents N --head SHA rep1.ncu-rep [rep2 ...]
 
 `launches`: the `--metrics gpu__time_duration.sum --csv --log-file` launch list -> per-kernel count,
 total, average and SHARE of the listed launches (cold-cache, serialised: compare shares only).
+`traffic`: the DRAM bytes (dram__bytes_read.sum, dram__bytes_write.sum) and duration of the first launch of every
+kernel in the given `ncu --set full` reports -> the small JSON bench.py reads for `roofline.traffic`.
 `kernel`: one `ncu --set full` report -> the counters DESIGN.md / bench.py quote (DRAM bytes, hit
 rates, issue utilisation, lane efficiency, pipe utilisation, stall mix) plus the hottest source lines.
 """
@@ -130,7 +133,42 @@ def kernel(src: str, dst: str, which: int | None) -> None:
     print(open(dst).read())
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+        "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3, "second": 1e6}
+
+
+def traffic(dst: str, reports, agents: int, head: str) -> None:
+    import json
+    kernels = {}
+    for src in reports:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rows = list(csv.reader(io.StringIO("\n".join(read_csv_after_preamble(raw)))))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        col = {h: i for i, h in enumerate(hdr)}
+        for r in data:
+            name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+            if name in kernels:
+                continue
+            val = lambda k: float(r[col[k]].replace(",", "")) * UNIT[units[col[k]]]  # noqa: E731
+            kernels[name] = {"dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
+                             "duration_us": val("gpu__time_duration.sum"), "agents": agents,
+                             "grid": r[col["Grid Size"]], "block": r[col["Block Size"]],
+                             "template": r[col["Kernel Name"]], "report": src}
+    doc = {"what": "per-launch DRAM traffic of the benched binary: one `ncu --set full --clock-control none` launch per "
+                   "kernel, python bench.py at its default workload; agents = live pedestrians of that launch",
+           "head": head, "agents_total": agents, "kernels": kernels}
+    open(dst, "w").write(json.dumps(doc, indent=1) + "\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "traffic":
+        a = sys.argv[2:]
+        agents = int(a[a.index("--agents") + 1])
+        head = a[a.index("--head") + 1] if "--head" in a else "?"
+        reps = [x for k, x in enumerate(a[1:], 1) if not x.startswith("--") and a[k - 1] not in ("--agents", "--head")]
+        traffic(a[0], reps, agents, head)
+        sys.exit(0)
     mode, src, dst = sys.argv[1:4]
     if mode == "launches":
         launches(src, dst)

@@ -169,3 +169,39 @@ def test_slabs_on_a_growing_non_uniform_crowd():
     assert max(per_slab) > 0 and sum(per_slab) == whole.model.get_pedestrian_count() > 6000
     whole.model.close()
     slabs.model.close()
+
+
+def test_top_slab_gains_immigrants_with_tight_bounds_and_no_spawns():
+    """Every slab is given ONLY the pedestrians of its own rows, with a capacity far below its population, so each
+    rebuild goes through the path that refreshes the host's population bound from the device before growing the
+    buffers (the bound is then exact). Everybody walks up: the top slab, whose arrays start at the halo capacity,
+    adopts immigrants every tick without any spawn. Its sort scratch (perm) is indexed with that offset and must
+    be sized with it (the overrun the round-1 advisor found); the result must equal the whole domain bit for bit."""
+    from pedoni_b200 import slab_rows
+    crowd = SyntheticCrowd(n=6000)
+    sc, field = crowd.scenario(), crowd.field()
+    pos, dest, vel, v0 = crowd.agents()
+    vel[:, 1] = 1.2
+    opts = SimulatorOptions()
+    whole = SocialForceModelCuda(opts, sc, field, math_mode=PEDONI_MATH_FAST)
+    slabs = SlabGroup(opts, sc, field, 2, math_mode=PEDONI_MATH_FAST, capacity=1024)
+    ny, _ = whole.grid_shape()
+    row = np.trunc(pos[:, 1] / np.float32(1.4)).astype(int)
+    whole.upload_state(pos, dest, vel, v0)
+    for r, s in enumerate(slabs.slabs):
+        r0, r1 = slab_rows(ny, 2, r)
+        mine = (row >= r0) & (row < r1)
+        s.upload_state(pos[mine], dest[mine], vel[mine], v0[mine])
+    top0 = None
+    for tick in range(20):
+        for m in (whole, slabs):
+            m.rebuild()
+        if top0 is None:
+            top0 = slabs.slabs[1].get_pedestrian_count()
+        np.testing.assert_array_equal(whole.cell_table(), slabs.cell_table(), err_msg=f"tick {tick}")
+        _assert_same(whole, slabs, f"after rebuild, tick {tick}")
+        for m in (whole, slabs):
+            m.step()
+    assert slabs.slabs[1].get_pedestrian_count() > top0 + 50  # net immigration into the top slab
+    whole.close()
+    slabs.close()
