@@ -384,12 +384,14 @@ def run_ours(args):
     if not args.no_e2e:
         cap = int(n0 * 1.02) + 8 * E2E_SPAWN_PER_STEP * (2 * (args.steps + args.warmup) + 8)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
-        h_pos, h_dest = pin((cap, 2), torch.float32), pin((cap,), torch.int32).view(np.uint32)
+        # list_pedestrians' payload: position + destination, the destination as one byte (pedoni_download_begin_u8)
+        h_pos, h_dest = pin((cap, 2), torch.float32), pin((cap,), torch.uint8)
         nb = E2E_SPAWN_PER_STEP
         s_pos, s_dest, s_v0 = pin((nb, 2), torch.float32), pin((nb,), torch.int32).view(np.uint32), \
             pin((nb,), torch.float32)
         extra = SyntheticCrowd(n=args.agents, density=args.density, seed=crowd.seed ^ 0xE2E)
-        h_pos2, h_dest2 = pin((cap, 2), torch.float32), pin((cap,), torch.int32).view(np.uint32)
+        h_pos2, h_dest2 = pin((cap, 2), torch.float32), pin((cap,), torch.uint8)
+        h_dest32 = pin((cap,), torch.int32).view(np.uint32)  # the blocking variant delivers the trait's 4-byte type
         bufs = [(h_pos, h_dest), (h_pos2, h_dest2)]
         state = {"inflight": 0, "n": 0, "bytes": 0}
 
@@ -413,7 +415,7 @@ def run_ours(args):
             while state["inflight"] > keep:
                 pos, dest = model.download_end()
                 state["n"] += pos.shape[0]
-                state["bytes"] = pos.shape[0] * model.download_wire_bytes()  # what crossed PCIe for this tick
+                state["bytes"] = pos.shape[0] * (8 + dest.itemsize)  # what crossed PCIe for this tick
                 state["inflight"] -= 1
 
         # the synthetic inflow (uniform over the domain) is drawn before the clock starts: generating random
@@ -466,17 +468,16 @@ def run_ours(args):
                "d2h_achieved_gbs": e_d2h / (e_ms / args.steps * 1e-3) / 1e9,
                "order": "eager" if eager else "plain",
                "timer": "host wall clock around the K ticks (device events cannot see the D2H stream)",
-               "api": "pedoni_spawn + pedoni_rebuild + pedoni_step + pedoni_download_begin/_end(pos, destination): "
+               "api": "pedoni_spawn + pedoni_rebuild + pedoni_step + pedoni_download_begin_u8/_end(pos f32x2, destination u8): "
                       "software pipeline: inside the clock, K ticks are computed (k+1 .. k+K) and K ticks' "
-                      "pedestrians are delivered to host buffers in the API's types (k .. k+K-1); the payload of "
-                      "tick k travels while tick k+1 is computed and tick k-1 is finished on the host (two "
-                      "downloads in flight; a whole-domain handle sends destinations as bytes and widens them on "
-                      "the host). d2h_ceiling_gbs = aggregate pinned D2H rate of this box with all N ranks copying "
+                      "pedestrians are delivered to pinned host buffers (k .. k+K-1); the payload of tick k travels "
+                      "while tick k+1 is computed and tick k-1 is finished on the host (two downloads in flight). "
+                      "d2h_ceiling_gbs = aggregate pinned D2H rate of this box with all N ranks copying "
                       "at once (8 x 64 MiB each)"}
 
         # ---- the reference's own call sequence: tick, whole list on the host, next tick (main.rs:86-97) --------
         kb = k0 + args.steps + 1
-        out = (h_pos, h_dest, None, None)
+        out = (h_pos, h_dest32, None, None)
 
         def blocking_tick(k):
             p, d, _, v = inflow[k]
@@ -515,7 +516,9 @@ def run_ours(args):
         if world > 1:  # the interior launch integrates the owned rows minus the two boundary rows each side
             agents_per_launch = min(agents_per_launch, agents_interior)
         achieved = ALGO_BYTES_PER_UPDATE * agents_per_launch / (force_ms * 1e-3) / 1e9
-        step_kernel_ms = {k[:-3]: prof[k] / args.steps for k in prof if k.endswith("_ms")}
+        step_kernel_ms = {name: prof[key] / args.steps for name, key in (
+            ("key", "key_ms"), ("sort", "gather_ms"), ("force", "force_ms"), ("force_edge", "force_edge_ms"),
+            ("pack", "pack_ms"), ("exchange_unpack", "comm_ms"))}
         per_update, traffic_doc = traffic_record()
         use_traffic = per_update is not None and args.math == "fast" and args.density == 1.0 and \
             args.agents == traffic_doc.get("agents_total")

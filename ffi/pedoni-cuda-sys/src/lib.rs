@@ -116,6 +116,7 @@ extern "C" {
     pub fn pedoni_count_published(model: *mut PedoniModel, count: *mut i32, rebuild_ordinal: *mut u32) -> c_int;
     pub fn pedoni_download_begin(model: *mut PedoniModel, pos_xy: *mut f32, destination: *mut u32, cap: u32) -> c_int;
     pub fn pedoni_download_end(model: *mut PedoniModel, n_out: *mut u32) -> c_int;
+    pub fn pedoni_download_begin_u8(model: *mut PedoniModel, pos_xy: *mut f32, destination8: *mut u8, cap: u32) -> c_int;
     pub fn pedoni_download_wire_bytes(model: *const PedoniModel) -> c_int;
     pub fn pedoni_observe(model: *mut PedoniModel, y0: f32, y1: f32, n_bins: u32, out: *mut PedoniObservables) -> c_int;
     pub fn pedoni_upload_state(model: *mut PedoniModel, n: u32, pos_xy: *const f32, destination: *const u32,

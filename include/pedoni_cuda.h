@@ -186,6 +186,10 @@ int pedoni_download(PedoniModel* model, float* pos_xy, uint32_t* destination, fl
  */
 int pedoni_download_begin(PedoniModel* model, float* pos_xy, uint32_t* destination, uint32_t cap);
 int pedoni_download_end(PedoniModel* model, uint32_t* n_out);
+/* The same with the destinations delivered as BYTES (9 instead of 12 bytes per pedestrian over PCIe, nothing to
+ * widen on the host; a caller that builds `Pedestrian { pos, destination: usize }` records touches every element
+ * anyway). Needs at most 256 potential maps (PEDONI_ERR_UNSUPPORTED otherwise). Completed by pedoni_download_end. */
+int pedoni_download_begin_u8(PedoniModel* model, float* pos_xy, uint8_t* destination8, uint32_t cap);
 
 /*
  * Aggregate observables reduced ON THE DEVICE instead of downloading every
@@ -238,9 +242,11 @@ int pedoni_field_build(float size_x, float size_y, float unit, int32_t n_obstacl
 
 typedef struct PedoniKernelTimes {
     /* accumulated since pedoni_profile_reset, milliseconds, measured with CUDA events.
-     * key = key_kernel (spawned / uploaded agents only); histogram = 0 (the per-cell count is fused into the
-     * force epilogue and key_kernel; kept for ABI stability); scan = the single-pass chained scan;
-     * force = interior + edge launches; comm = exchange + unpack on the edge stream (overlaps force). */
+     * key = key_kernel (spawned / uploaded agents only); gather = sort_cells_kernel, the whole rebuild (chained scan
+     * over the cell populations + stable reorder of the state, one launch); histogram, scan and scatter = 0 (the
+     * per-cell count and the cell membership are fused into the force epilogue and key_kernel, the scan and the
+     * scatter into the sort; kept for ABI stability); force: see below; comm = exchange + unpack on the edge stream
+     * (overlaps force). */
     double key_ms, histogram_ms, scan_ms, scatter_ms, gather_ms, force_ms, comm_ms;
     uint64_t key_launches, histogram_launches, scan_launches, scatter_launches, gather_launches,
         force_launches, comm_launches;
@@ -252,7 +258,7 @@ typedef struct PedoniKernelTimes {
     uint64_t force_edge_launches, pack_launches;
 } PedoniKernelTimes;
 
-/* One timed launch (profiling on): kind = 0 key, 2 scan, 3 scatter, 4 gather, 5 force (interior), 6 exchange +
+/* One timed launch (profiling on): kind = 0 key, 4 sort (the rebuild), 5 force (interior), 6 exchange +
  * unpack, 7 force (edge rows), 8 pack; stream = 0 main, 1 edge; start / stop in milliseconds after the
  * last pedoni_timer_begin (CUDA events; both streams share the origin). */
 typedef struct PedoniLaunchRecord {

@@ -94,6 +94,7 @@ SIGNATURES = {
     "pedoni_download": (C.c_int, [C.c_void_p, c_float_p, c_u32_p, c_float_p, c_float_p, C.c_uint32, c_u32_p]),
     "pedoni_download_begin": (C.c_int, [C.c_void_p, c_float_p, c_u32_p, C.c_uint32]),
     "pedoni_download_end": (C.c_int, [C.c_void_p, c_u32_p]),
+    "pedoni_download_begin_u8": (C.c_int, [C.c_void_p, c_float_p, C.POINTER(C.c_uint8), C.c_uint32]),
     "pedoni_observe": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_uint32, C.POINTER(PedoniObservables)]),
     "pedoni_upload_state": (C.c_int, [C.c_void_p, C.c_uint32, c_float_p, c_u32_p, c_float_p, c_float_p]),
     "pedoni_grid_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -85,15 +85,15 @@ static_assert(kWarpSmemBytes % 16 == 0, "warp slices stay 16-byte aligned");
 struct ForceParams {
     AgentArrays in;              // cell-sorted state (pre-integration)
     AgentArrays out;             // integrated state, same indexing
-    const uint32_t* d_range;     // device [begin, end): agents this launch integrates
+    const uint32_t* d_range;     // device [begin, end): agents this launch integrates (CTAs with blockIdx.y == 0)
+    const uint32_t* d_range_hi;  // a second range for the CTAs with blockIdx.y == 1 (both edges of a slab in one launch)
     const uint32_t* d_owned;     // device [begin, end): agents this handle owns (the updates counter counts these)
     uint32_t count_upper;        // host upper bound of end - begin (grid size)
     const uint32_t* cell_start;  // local cell table (neighbor_grid_indices, sfm.rs:22)
     GridView grid;
     FieldView field;
-    uint32_t* keys_out;          // next rebuild's keys, indexed like the arrays
-    uint32_t* ticket_out;        // next rebuild's in-cell slots (the histogram is fused here)
-    uint32_t* cell_count;        // per-cell population of the NEXT rebuild (zeroed by the previous one)
+    const uint32_t* d_compute;   // device [begin, end) of the next rebuild's resident segment: logical index = id - begin
+    CellSort cs;                 // the next rebuild's cell membership (the enrolment is fused here)
     uint32_t* error_flag;
     unsigned long long* updates_total;  // += owned agents of this launch (thread 0 of block 0)
     unsigned long long* arrived;        // [16] cumulative arrivals by destination (owned agents only)
@@ -248,6 +248,12 @@ __device__ __forceinline__ void footprint_gather(cudaTextureObject_t tex, int x0
         }
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // sm_100: one FMNMX3; NaN operands are skipped
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // `tile`: texel offset of the map inside the atlas (kTex only).
 template <Math M, bool WithCentre, bool kTex>
 __device__ __forceinline__ void field_gradient(const float* __restrict__ g, cudaTextureObject_t tex, int2 tile, int ny, int nx,
@@ -270,11 +276,14 @@ __device__ __forceinline__ void field_gradient(const float* __restrict__ g, cuda
             }
             // (The max over all 16 texels also keeps the 16 loads in flight together: testing a single
             // central texel is 15 instructions shorter and measurably SLOWER, 0.846 vs 0.809 ms at 10 M.)
-            float big = 0.0f;
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) big = fmaxf(big, t[r][c]);
+            float big = fmax3(t[0][0], t[0][1], t[0][2]);  // FMNMX3: 8 instructions for the 16 texels
+            big = fmax3(big, t[0][3], t[1][0]);
+            big = fmax3(big, t[1][1], t[1][2]);
+            big = fmax3(big, t[1][3], t[2][0]);
+            big = fmax3(big, t[2][1], t[2][2]);
+            big = fmax3(big, t[2][3], t[3][0]);
+            big = fmax3(big, t[3][1], t[3][2]);
+            big = fmaxf(big, t[3][3]);
             if (big < noise_limit) {
             // u[r][c] = sum_b sum_a wy_b wx_a t[r+b][c+a]; gx = sum_r k_r (u[r][0] - u[r][2]), k = (1, 2, 1)
             float h[4], v[4];
@@ -484,7 +493,8 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     float2* tile_vel = tile_pos + kTileAlloc;
     (void)tile_vel;  // only the cp.async staging variant names it
 
-    const uint32_t begin = p.d_range[0], end = p.d_range[1];
+    const uint32_t* range = blockIdx.y == 0 ? p.d_range : p.d_range_hi;
+    const uint32_t begin = range[0], end = range[1];
     const uint32_t block_first = begin + blockIdx.x * kForceThreads;
     if (block_first >= end) return;  // whole CTA beyond the live range (grids are sized from an upper bound)
     const uint32_t warp_first = block_first + warp * 32;
@@ -521,17 +531,18 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
         row = c.y;
         const int ly = c.y - p.grid.row_base;
         const int x_start = min(max(c.x - 1, 0), p.grid.nx - 1), x_end = max(min(c.x + 1, p.grid.nx - 1), 0);
+        const uint32_t unx = static_cast<uint32_t>(p.grid.nx), table_end = static_cast<uint32_t>(p.grid.table_rows) * unx;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
+            // Two unconditional loads per row with selected 32-bit indices. A row off the table is an empty range,
+            // placed (table start / table end) so that the warp's windows stay monotone.
             const int y = ly + d - 1;
-            if (y >= 0 && y < p.grid.table_rows) {
-                const uint32_t* rowp = p.cell_start + static_cast<size_t>(y) * p.grid.nx;
-                r_beg[d] = __ldg(rowp + x_start);
-                r_end[d] = __ldg(rowp + x_end + 1);
-            } else {  // off the grid: an empty range, placed so that the windows stay monotone
-                const size_t at = (y < 0) ? 0 : static_cast<size_t>(p.grid.table_rows) * p.grid.nx;
-                r_beg[d] = r_end[d] = __ldg(p.cell_start + at);
-            }
+            const uint32_t row0 = static_cast<uint32_t>(y) * unx;
+            const bool below = y < 0, above = y >= p.grid.table_rows;
+            const uint32_t ib = below ? 0u : (above ? table_end : row0 + static_cast<uint32_t>(x_start));
+            const uint32_t ie = below ? 0u : (above ? table_end : row0 + static_cast<uint32_t>(x_end) + 1u);
+            r_beg[d] = __ldg(p.cell_start + ib);
+            r_end[d] = __ldg(p.cell_start + ie);
         }
     }
 
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
         int2 tile = make_int2(0, 0);
         if (kTex) {
             const int t = 1 + static_cast<int>(dest);
-            tile = make_int2((t % p.field.atlas_tiles_x) * p.field.fx, (t / p.field.atlas_tiles_x) * p.field.fy);
+            tile = make_int2((t & (p.field.atlas_tiles_x - 1)) * p.field.fx, (t >> p.field.atlas_shift) * p.field.fy);
         }
         field_gradient<M, false, kTex>(p.field.potential_maps + static_cast<size_t>(dest) * p.field.fy * p.field.fx,
                                        p.field.atlas, tile, p.field.fy, p.field.fx, q, noise_limit, flat_limit2, gx, gy, unused);
@@ -703,8 +714,8 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     p.out.dest[id] = dest;
     // ghost-row agents are integrated twice (here and by their owner): only the owner counts an arrival
     const bool owned = id >= p.d_owned[0] && id < p.d_owned[1];
-    count_key(sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned, kTex), p.cell_count, p.keys_out + id,
-              p.ticket_out + id);
+    enroll(p.cs, sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned, kTex), id - p.d_compute[0],
+           p.error_flag);
     // Slab handles exchange two ghost rows per tick, which covers every move of less than one grid row
     // (1.4 m per 0.1 s); anything faster would silently vanish at a slab boundary, so flag it.
     if (p.grid.slab) {

@@ -4,18 +4,14 @@
 // Replaces NeighborGrid::update (neighbor_grid.rs:22-36) and the serial walk/gather of
 // SocialForceModel::spawn_pedestrians (sfm.rs:58-77):
 //
-//   key        cell key per agent + per-cell population (atomicAdd on the cell counter; the returned
-//              ticket is a unique but order-arbitrary slot inside the cell). Fused into the force kernel's
-//              epilogue for agents that were just integrated; key_kernel only handles freshly spawned /
-//              uploaded agents. The counters are zeroed at the end of every rebuild.
-//   scan       exclusive prefix over cells, built from block-wide scans -> `neighbor_grid_indices`
-//              (sfm.rs:61-75), length cells + 1
-//   scatter    perm[start[cell] + ticket] = logical input index
-//   gather     rank-by-counting inside the cell: an agent's final slot is start[cell] + #{members of
-//              the cell with a smaller input index}. That is exactly "within a cell, ascending
-//              previous index" (sfm.rs:66-68) and makes the output independent of the atomic
-//              arrival order, i.e. run-to-run deterministic. Then one coalesced read / near-coalesced
-//              write of the 24-byte state into the other buffer.
+//   enrol      every pedestrian takes an atomic ticket on the counter of the cell it will belong to and leaves its
+//              logical input index in the cell's slot row. Fused into the force kernel's epilogue for pedestrians
+//              that were just integrated; key_kernel only handles freshly spawned / uploaded ones.
+//   sort       ONE kernel (sort_cells_kernel): chained prefix scan over the cell populations ->
+//              `neighbor_grid_indices` (sfm.rs:61-75, length cells + 1); then, per output slot, the member of the
+//              cell with exactly `rank` smaller input indices — "within a cell, ascending previous index"
+//              (sfm.rs:66-68), independent of the atomic arrival order, i.e. run-to-run deterministic — and one
+//              gathered read / coalesced write of the 24-byte state into the other buffer.
 //
 // The sort input is a virtual concatenation of segments (the resident agents this handle just
 // integrated — its owned rows plus, on a slab handle, one ghost row each side — then the appended
@@ -56,8 +52,6 @@ constexpr int kMaxSegments = 2;
 
 struct Segment {
     AgentArrays a;
-    uint32_t* keys;           // sort keys, indexed like the arrays
-    uint32_t* ticket;         // slot inside the cell (kKeyDrop: not kept), indexed like the arrays
     const uint32_t* d_range;  // device: [begin, end) of live entries inside the arrays; nullptr = [0, upper)
     uint32_t upper;           // host-known upper bound of (end - begin)
 };
@@ -73,8 +67,6 @@ struct SortInput {
 // parameter, which would force a local-memory copy).
 struct Located {
     AgentArrays a;
-    uint32_t* keys;
-    uint32_t* ticket;
     uint32_t idx;
     bool live;
 };
@@ -87,8 +79,6 @@ __device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
     r.a.vel = second ? in.seg[1].a.vel : in.seg[0].a.vel;
     r.a.v0 = second ? in.seg[1].a.v0 : in.seg[0].a.v0;
     r.a.dest = second ? in.seg[1].a.dest : in.seg[0].a.dest;
-    r.keys = second ? in.seg[1].keys : in.seg[0].keys;
-    r.ticket = second ? in.seg[1].ticket : in.seg[0].ticket;
     const uint32_t* d_range = second ? in.seg[1].d_range : in.seg[0].d_range;
     // d_range == nullptr: the population is host-known, [0, upper) (appended spawns).
     uint32_t begin = 0, end = second ? in.seg[1].upper : in.seg[0].upper;
@@ -144,17 +134,48 @@ __global__ void __launch_bounds__(256) spawn_groups_kernel(AgentArrays out, uint
     out.dest[at + j] = G.destination;
 }
 
-// Key + population count of one agent: shared by key_kernel and the force kernel's epilogue.
-__device__ __forceinline__ void count_key(uint32_t key, uint32_t* __restrict__ cell_count, uint32_t* key_slot,
-                                          uint32_t* ticket_slot) {
-    *key_slot = key;
-    *ticket_slot = key < kKeyFirstSpecial ? atomicAdd(cell_count + key, 1u) : kKeyDrop;
+// ---- cell membership, written by the producers of the next rebuild -----------------------------------------
+// A pedestrian ENROLS in the cell it will belong to: an atomic ticket on the cell's counter and its logical
+// sort-input index t stored in the cell's slot row (kSlotsPerCell entries = one 32-byte sector per cell). Members
+// beyond the row (a jam: more than 8 pedestrians on 1.96 m^2) go to a per-cell chain in an overflow list. The
+// producers are the force kernel's epilogue (resident pedestrians, keyed on their just-integrated position) and
+// key_kernel (freshly spawned / uploaded ones); the consumer is sort_cells_kernel, which therefore needs no
+// per-pedestrian key, ticket or permutation arrays at all.
+constexpr int kSlotsPerCell = 8;
+
+struct OverflowEntry {
+    uint32_t t;     // logical sort-input index of the member
+    uint32_t next;  // 1-based index of the next entry of the same cell, 0 = end of chain
+};
+
+struct CellSort {
+    uint32_t* cell_count;  // [cells] tickets handed out = population of the cell in the NEXT table (zeroed by the sort)
+    uint32_t* slots;       // [cells][kSlotsPerCell] t of the member holding ticket j < kSlotsPerCell
+    uint32_t* ovf_head;    // [cells] chain of the members with ticket >= kSlotsPerCell (reset by the sort)
+    OverflowEntry* ovf;    // [ovf_cap]
+    uint32_t* ovf_count;   // entries in use (reset by the sort)
+    uint32_t ovf_cap;      // = capacity of the agent arrays: every pedestrian could overflow
+};
+
+__device__ __forceinline__ void enroll(const CellSort& cs, uint32_t key, uint32_t t, uint32_t* error_flag) {
+    if (key >= kKeyFirstSpecial) return;  // dropped: outside the grid, despawned, or another slab's row
+    const uint32_t ticket = atomicAdd(cs.cell_count + key, 1u);
+    if (ticket < static_cast<uint32_t>(kSlotsPerCell)) {
+        cs.slots[static_cast<size_t>(key) * kSlotsPerCell + ticket] = t;
+    } else {
+        const uint32_t e = atomicAdd(cs.ovf_count, 1u);
+        if (e < cs.ovf_cap) {
+            cs.ovf[e].t = t;
+            cs.ovf[e].next = atomicExch(cs.ovf_head + key, e + 1u);
+        } else {
+            atomicOr(error_flag, kErrSortOverflow);  // cannot happen with ovf_cap = array capacity
+        }
+    }
 }
 
-// ---- key: only for logical indices in [t_begin, t_end) whose keys are not fresh -------------------
+// ---- key: only for logical indices in [t_begin, t_end) that the force kernel has not enrolled ------------
 __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin, uint32_t t_end, GridView g,
-                                                  FieldView f, uint32_t* __restrict__ cell_count,
-                                                  uint32_t* __restrict__ error_flag,
+                                                  FieldView f, CellSort cs, uint32_t* __restrict__ error_flag,
                                                   unsigned long long* __restrict__ arrived) {
     uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
@@ -165,26 +186,9 @@ __global__ void __launch_bounds__(256) key_kernel(SortInput in, uint32_t t_begin
     // a replicated spawn that stands on its destination is counted as arrived by the slab owning its row
     const float2 pos = l.a.pos[l.idx];
     const int row = __float2int_rz(S::div(pos.y, g.unit));
-    count_key(sort_key(g, f, pos, l.a.dest[l.idx], error_flag, arrived, row >= g.own_row0 && row < g.own_row1),
-              cell_count, l.keys + l.idx, l.ticket + l.idx);
+    enroll(cs, sort_key(g, f, pos, l.a.dest[l.idx], error_flag, arrived, row >= g.own_row0 && row < g.own_row1), t,
+           error_flag);
 }
-
-// ---- scan: exclusive prefix over n_cells counters in ONE pass (chained scan over tile aggregates) -------
-// A tile = 1024 threads x 16 cells (10 M pedestrians = 5.1 M cells = 312 tiles). Tiles are handed out by an atomic ticket (so a tile only ever waits for
-// tiles whose CTAs are already running), publish their aggregate in a 64-bit status word tagged with the
-// tick (no reset between launches), and sum their predecessors' aggregates for the exclusive prefix. The
-// same pass
-//   - zeroes the counters for the next tick's fused histogram (force epilogue / key_kernel),
-//   - writes the layout ranges that depend on the owned rows (the thread that produces the cell-start
-//     they are read from writes them), and
-//   - publishes the owned population to the host: one aligned 64-bit store to pinned memory,
-//     tick << 32 | n_owned, so a lagging reader never sees a torn pair.
-constexpr int kScanThreads = 1024;
-#ifndef PEDONI_SCAN_ITEMS
-#define PEDONI_SCAN_ITEMS 16
-#endif
-constexpr int kScanItems = PEDONI_SCAN_ITEMS;
-constexpr int kScanTile = kScanThreads * kScanItems;  // cells per block
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -215,7 +219,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* b
     return excl;
 }
 
-struct ScanLayout {  // what the scan publishes besides the table (see RangeId)
+struct ScanLayout {  // what the sort publishes besides the table (see RangeId)
     uint32_t own_begin_cell, own_end_cell, nx;
     int has_below, has_above;
     uint32_t* ranges;
@@ -223,7 +227,7 @@ struct ScanLayout {  // what the scan publishes besides the table (see RangeId)
     uint32_t tick;
 };
 
-constexpr unsigned long long kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62;
+constexpr unsigned long long kScanAggregate = 1ull << 62;
 __device__ __forceinline__ unsigned long long scan_status(unsigned long long flag, uint32_t tick, uint32_t value) {
     return flag | (static_cast<unsigned long long>(tick & 0x3FFFFFFFu) << 32) | value;
 }
@@ -244,239 +248,317 @@ __device__ __forceinline__ void publish_cell_start(const ScanLayout& L, uint32_t
     if (L.has_above && cell == L.own_end_cell - L.nx) L.ranges[2 * kRangeInterior + 1] = start;
 }
 
-// cell_start[c] = offset + exclusive prefix; cell_start[n_cells] = offset + total. `offset` is the halo
-// capacity H on a slab handle with a neighbour below (owned agents start at H), 0 otherwise.
-__global__ void __launch_bounds__(kScanThreads) scan_cells_kernel(uint32_t* __restrict__ cell_count, uint32_t n_cells,
-                                                                  uint32_t offset, uint32_t* __restrict__ cell_start,
-                                                                  unsigned long long* __restrict__ tile_status,
-                                                                  uint32_t* __restrict__ tile_ticket, uint32_t n_tiles,
-                                                                  ScanLayout L) {
-    __shared__ uint32_t s_tile, s_total, s_prefix;
-    if (threadIdx.x == 0) {
-        s_tile = atomicAdd(tile_ticket, 1u);
-        if (s_tile == n_tiles - 1) *tile_ticket = 0;  // every ticket of this launch has been taken
-    }
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint32_t sum = 0;
-    if (base + kScanItems <= n_cells) {
-        uint4* p = reinterpret_cast<uint4*>(cell_count + base);
-#pragma unroll
-        for (int q = 0; q < kScanItems / 4; ++q) {
-            const uint4 a = p[q];
-            v[4 * q] = a.x, v[4 * q + 1] = a.y, v[4 * q + 2] = a.z, v[4 * q + 3] = a.w;
-            p[q] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            v[k] = (base + k < n_cells) ? cell_count[base + k] : 0u;
-            if (base + k < n_cells) cell_count[base + k] = 0u;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) sum += v[k];
-    const uint32_t excl = block_exclusive_scan(sum, &s_total);
+// ---- the rebuild: ONE kernel, cell-centric ----------------------------------------------------------------------
+// Replaces NeighborGrid::update + the serial walk of spawn_pedestrians (neighbor_grid.rs:22-36, sfm.rs:58-77).
+// Persistent CTAs take tiles of kSortTile consecutive cells by ticket; a thread owns kSortItems consecutive cells.
+// Per tile:
+//   1. load (and zero, for the next tick) the cell populations and request the cells' slot rows; block scan; publish
+//      the tile aggregate in a tick-tagged status word and sum ALL predecessors' aggregates in one round of loads
+//      (tickets are handed out in order, so every predecessor is held by a running CTA or done: the spin cannot
+//      deadlock) -> `neighbor_grid_indices` (sfm.rs:61-75) for the tile's cells;
+//   2. warp by warp, 32 cells at a time: every cell's slot row is sorted ("within a cell, ascending previous index",
+//      sfm.rs:66-68; independent of the order in which the atomics handed out the tickets, hence run-to-run
+//      deterministic and identical across slab decompositions) and its members are staged by output slot;
+//   3. one pass over the staged indices moves the 24-byte state: gathered reads (near-sequential: a pedestrian moves
+//      less than a cell per tick), fully coalesced writes — the tile's pedestrians are one contiguous output range.
+//   The same pass writes the layout ranges that depend on the owned rows and publishes the owned population to the
+//   host (one aligned 64-bit store to pinned memory, tick << 32 | n_owned).
+// Cells holding more than kSlotsPerCell pedestrians find their extra members by walking the cell's overflow chain:
+// O(n^2) per cell, bounded, exact — a dense jam costs a few hundred instructions per pedestrian, nothing more.
+#ifndef PEDONI_SORT_THREADS
+#define PEDONI_SORT_THREADS 512
+#endif
+constexpr int kSortCtaThreads = PEDONI_SORT_THREADS;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortCtaThreads * kSortItems;  // cells per tile
+#ifndef PEDONI_SORT_UNROLL
+#define PEDONI_SORT_UNROLL 2  // pedestrians in flight per thread in the move pass (B200, 10 M: 2 -> 0.196 ms, 4 -> 0.207)
+#endif
+constexpr int kSortUnroll = PEDONI_SORT_UNROLL;
+#ifndef PEDONI_SORT_STAGE
+#define PEDONI_SORT_STAGE (PEDONI_SORT_THREADS * 20)  // output slots staged per round: a tile of 4096 cells holds ~8 000 pedestrians at 1 /m^2
+#endif
+constexpr int kSortStage = PEDONI_SORT_STAGE;
+constexpr size_t kSortSmemBytes = sizeof(uint32_t) * (kSortCtaThreads * kSlotsPerCell + kSortTile + 4 + kSortStage);
+#ifndef PEDONI_SORT_MIN_BLOCKS
+#define PEDONI_SORT_MIN_BLOCKS 2
+#endif
 
-    // Exclusive prefix of the tile: every predecessor's aggregate, fetched in ONE round of loads spread over
-    // the block (no chain of dependent round trips through earlier tiles' prefixes).
-    // Predecessors hold smaller tickets, so their CTAs are running or done: the spin cannot deadlock.
-    {
-        volatile unsigned long long* status = tile_status;
-        const unsigned long long tag = scan_status(kScanAggregate, L.tick, 0u) >> 32;
-        if (threadIdx.x == 0) {
-            s_prefix = 0;
-            status[tile] = scan_status(kScanAggregate, L.tick, s_total);
+struct SortScratch {
+    unsigned long long* tile_status;  // [n_tiles] tick-tagged aggregates (never reset)
+    uint32_t* tile_ticket;            // [2] tile counters; launch k uses [k & 1] and zeroes the other one
+    uint32_t* done_count;             // CTAs of this launch that have finished (the last one resets the overflow list)
+    uint32_t n_tiles;
+    uint32_t parity;
+};
+
+// The member of `cell` with exactly `rank` smaller logical indices among its n members.
+__device__ __forceinline__ uint32_t select_member(const CellSort& cs, uint32_t cell, uint32_t n, uint32_t rank, uint4 lo,
+                                                  uint4 hi) {
+    uint32_t m[kSlotsPerCell] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int a = 0; a < kSlotsPerCell; ++a)
+        if (static_cast<uint32_t>(a) >= n) m[a] = 0xFFFFFFFFu;  // unused slots hold stale values
+    uint32_t t = m[0];
+    if (n <= static_cast<uint32_t>(kSlotsPerCell)) {
+#pragma unroll
+        for (int a = 1; a < kSlotsPerCell; ++a) {
+            if (static_cast<uint32_t>(a) < n) {  // uniform over the threads that share the cell
+                uint32_t smaller = 0;
+#pragma unroll
+                for (int b = 0; b < kSlotsPerCell; ++b) smaller += (m[b] < m[a]) ? 1u : 0u;
+                if (smaller == rank) t = m[a];
+            }
+        }
+        return t;  // m[0] unless another member has the rank
+    }
+    // jam: the members beyond the slot row hang on the cell's chain
+    const uint32_t head = cs.ovf_head[cell];
+    auto smaller_than = [&](uint32_t x) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int b = 0; b < kSlotsPerCell; ++b) c += (m[b] < x) ? 1u : 0u;
+        uint32_t guard = n;
+        for (uint32_t e = head; e != 0 && guard-- != 0; e = cs.ovf[e - 1].next) c += (cs.ovf[e - 1].t < x) ? 1u : 0u;
+        return c;
+    };
+#pragma unroll
+    for (int a = 0; a < kSlotsPerCell; ++a)  // unrolled: m[] stays in registers
+        if (smaller_than(m[a]) == rank) return m[a];
+    uint32_t guard = n;
+    for (uint32_t e = head; e != 0 && guard-- != 0; e = cs.ovf[e - 1].next) {
+        const uint32_t x = cs.ovf[e - 1].t;
+        if (smaller_than(x) == rank) return x;
+    }
+    return t;  // unreachable with a consistent chain
+}
+
+__global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
+    sort_cells_kernel(SortInput in, CellSort cs, uint32_t n_cells, uint32_t offset, uint32_t* __restrict__ cell_start,
+                      SortScratch sc, ScanLayout L, AgentArrays out) {
+    // dynamic shared memory, see kSortSmemBytes
+    extern __shared__ __align__(16) uint32_t sort_smem[];
+    uint32_t* const s_sorted = sort_smem;                                 // per warp: 32 sorted slot rows
+    uint32_t* const s_start = s_sorted + kSortCtaThreads * kSlotsPerCell;  // [kSortTile + 1] starts of the tile's cells,
+                                                                           // relative to the tile's first pedestrian
+    uint32_t* const s_member = s_start + kSortTile + 4;  // [kSortStage] logical input index going to each staged slot
+    __shared__ uint32_t s_tile, s_total, s_prefix;
+    const uint32_t tid = threadIdx.x;
+    uint32_t* const ticket = sc.tile_ticket + sc.parity;
+    if (blockIdx.x == 0 && tid == 0) sc.tile_ticket[sc.parity ^ 1u] = 0;  // the next launch's counter, idle now
+
+    for (;;) {
+        __syncthreads();  // the previous tile's shared state is no longer read
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= sc.n_tiles) break;
+
+        // ---- 1. populations -> starts
+        const uint32_t base = tile * kSortTile + tid * kSortItems;
+        uint32_t v[kSortItems];
+        if (base + kSortItems <= n_cells) {
+            uint4* p = reinterpret_cast<uint4*>(cs.cell_count + base);
+#pragma unroll
+            for (int q = 0; q < kSortItems / 4; ++q) {
+                const uint4 a = p[q];
+                v[4 * q] = a.x, v[4 * q + 1] = a.y, v[4 * q + 2] = a.z, v[4 * q + 3] = a.w;
+                p[q] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSortItems; ++k) {
+                v[k] = (base + k < n_cells) ? cs.cell_count[base + k] : 0u;
+                if (base + k < n_cells) cs.cell_count[base + k] = 0u;
+            }
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) sum += v[k];
+        const uint32_t excl = block_exclusive_scan(sum, &s_total);
+        {
+            volatile unsigned long long* status = sc.tile_status;
+            const unsigned long long tag = scan_status(kScanAggregate, L.tick, 0u) >> 32;
+            if (tid == 0) {
+                s_prefix = 0;
+                status[tile] = scan_status(kScanAggregate, L.tick, s_total);
+            }
+            __syncthreads();
+            uint32_t part = 0;
+            for (uint32_t j = tid; j < tile; j += kSortCtaThreads) {
+                unsigned long long st;
+                do {
+                    st = status[j];
+                } while ((st >> 32) != tag);
+                part += static_cast<uint32_t>(st);
+            }
+            part = __reduce_add_sync(0xFFFFFFFFu, part);
+            if ((tid & 31) == 0 && part != 0) atomicAdd(&s_prefix, part);
         }
         __syncthreads();
-        uint32_t part = 0;
-        for (uint32_t j = threadIdx.x; j < tile; j += kScanThreads) {
-            unsigned long long st;
-            do {
-                st = status[j];
-            } while ((st >> 32) != tag);
-            part += static_cast<uint32_t>(st);
-        }
-        part = __reduce_add_sync(0xFFFFFFFFu, part);
-        if ((threadIdx.x & 31) == 0 && part != 0) atomicAdd(&s_prefix, part);
-    }
-    __syncthreads();
-
-    uint32_t run = offset + s_prefix + excl;
-    if (base + kScanItems <= n_cells) {
-        // 16-byte stores: scalar ones reach L2 as one partial-sector write per cell
-        uint32_t start[kScanItems];
+        const uint32_t tile_base = offset + s_prefix;  // index of the tile's first pedestrian in the new arrays
+        {
+            uint32_t run = excl;
+            uint32_t start[kSortItems];
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            start[k] = run;
-            publish_cell_start(L, base + k, run);
-            run += v[k];
-        }
-        uint4* p = reinterpret_cast<uint4*>(cell_start + base);
-#pragma unroll
-        for (int q = 0; q < kScanItems / 4; ++q)
-            p[q] = make_uint4(start[4 * q], start[4 * q + 1], start[4 * q + 2], start[4 * q + 3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            if (base + k < n_cells) {
-                cell_start[base + k] = run;
-                publish_cell_start(L, base + k, run);
+            for (int k = 0; k < kSortItems; ++k) {
+                start[k] = tile_base + run;
+                s_start[tid * kSortItems + k] = run;
+                if (base + k < n_cells) publish_cell_start(L, base + k, tile_base + run);
+                run += v[k];
             }
-            run += v[k];
-        }
-    }
-    if (base < n_cells && base + kScanItems >= n_cells) {
-        cell_start[n_cells] = run;
-        publish_cell_start(L, n_cells, run);
-    }
-}
-
-// ---- scatter: perm[start[cell] + ticket] = t -----------------------------------------------------
-__device__ __forceinline__ void scatter_one(const SortInput& in, uint32_t t, const uint32_t* __restrict__ cell_start,
-                                            uint32_t* __restrict__ perm) {
-    const Located l = locate(in, t);
-    if (!l.live) return;
-    const uint32_t tk = l.ticket[l.idx];
-    if (tk == kKeyDrop) return;
-    perm[cell_start[l.keys[l.idx]] + tk] = t;
-}
-
-// Elements per thread, strided by the block so every access stays coalesced. The scatter is a chain of
-// dependent loads (key -> cell start -> slot): two chains per thread keep the memory system busier (B200,
-// 10 M: 0.057 -> 0.044 ms). The gather wants the opposite: one element per thread and <= 32 registers for full
-// occupancy, with the 24-byte state loaded BEFORE the key -> cell start -> rank chain (0.187 -> 0.127 ms;
-// 2 / 4 / 8 elements: 0.140 / 0.162 / 0.255 ms).
-#ifndef PEDONI_SCATTER_ITEMS
-#define PEDONI_SCATTER_ITEMS 2
-#endif
-#ifndef PEDONI_GATHER_ITEMS
-#define PEDONI_GATHER_ITEMS 1
-#endif
-constexpr int kSortThreads = 256;
-constexpr int kScatterItems = PEDONI_SCATTER_ITEMS, kScatterTile = kSortThreads * kScatterItems;
-constexpr int kGatherItems = PEDONI_GATHER_ITEMS, kGatherTile = kSortThreads * kGatherItems;
-
-__global__ void __launch_bounds__(kSortThreads) scatter_kernel(SortInput in, uint32_t total_upper,
-                                                               const uint32_t* __restrict__ cell_start,
-                                                               uint32_t* __restrict__ perm) {
-    const uint32_t t0 = blockIdx.x * kScatterTile + threadIdx.x;
-    uint32_t key[kScatterItems], tk[kScatterItems], start[kScatterItems];
+            if (base + kSortItems <= n_cells) {
+                // 16-byte stores: scalar ones reach L2 as one partial-sector write per cell
+                uint4* p = reinterpret_cast<uint4*>(cell_start + base);
 #pragma unroll
-    for (int k = 0; k < kScatterItems; ++k) {
-        const uint32_t t = t0 + k * kSortThreads;
-        tk[k] = kKeyDrop;
-        key[k] = 0;
-        if (t < total_upper) {
-            const Located l = locate(in, t);
-            if (l.live) tk[k] = l.ticket[l.idx], key[k] = l.keys[l.idx];
-        }
-    }
+                for (int q = 0; q < kSortItems / 4; ++q)
+                    p[q] = make_uint4(start[4 * q], start[4 * q + 1], start[4 * q + 2], start[4 * q + 3]);
+            } else {
 #pragma unroll
-    for (int k = 0; k < kScatterItems; ++k) start[k] = tk[k] != kKeyDrop ? cell_start[key[k]] : 0u;
-#pragma unroll
-    for (int k = 0; k < kScatterItems; ++k)
-        if (tk[k] != kKeyDrop) perm[start[k] + tk[k]] = t0 + k * kSortThreads;
-}
-
-// ---- gather: stable rank inside the cell, then move the 24-byte state ----------------------------
-__device__ __forceinline__ void gather_one(const SortInput& in, uint32_t t, const uint32_t* __restrict__ cell_start,
-                                           const uint32_t* __restrict__ perm, const AgentArrays& out) {
-    const Located l = locate(in, t);
-    if (!l.live) return;
-    const uint32_t idx = l.idx;
-    const uint32_t key = l.keys[idx];
-    if (key >= kKeyFirstSpecial) return;  // count_key: exactly the entries whose ticket is kKeyDrop
-    const uint32_t begin = cell_start[key], end = cell_start[key + 1];
-    uint32_t rank = 0;
-    for (uint32_t j = begin; j < end; ++j) rank += (perm[j] < t) ? 1u : 0u;
-    const uint32_t dst = begin + rank;
-    const AgentArrays& a = l.a;
-    out.pos[dst] = a.pos[idx];
-    out.vel[dst] = a.vel[idx];
-    out.v0[dst] = a.v0[idx];
-    out.dest[dst] = a.dest[idx];
-}
-
-__global__ void __launch_bounds__(kSortThreads) gather_kernel(SortInput in, uint32_t total_upper,
-                                                              const uint32_t* __restrict__ cell_start,
-                                                              const uint32_t* __restrict__ perm, AgentArrays out) {
-    const uint32_t t0 = blockIdx.x * kGatherTile + threadIdx.x;
-    uint32_t key[kGatherItems], begin[kGatherItems], end[kGatherItems], dest[kGatherItems];
-    bool keep[kGatherItems];
-    float2 pos[kGatherItems], vel[kGatherItems];
-    float v0[kGatherItems];
-    // every load that does not depend on another one first: key, ticket and the 24-byte state
-#pragma unroll
-    for (int k = 0; k < kGatherItems; ++k) {
-        const uint32_t t = t0 + k * kSortThreads;
-        keep[k] = false;
-        key[k] = 0;
-        if (t < total_upper) {
-            const Located l = locate(in, t);
-            if (l.live) {
-                key[k] = l.keys[l.idx];
-                keep[k] = key[k] < kKeyFirstSpecial;  // count_key: exactly the entries that hold a ticket
-                pos[k] = l.a.pos[l.idx];
-                vel[k] = l.a.vel[l.idx];
-                v0[k] = l.a.v0[l.idx];
-                dest[k] = l.a.dest[l.idx];
+                for (int k = 0; k < kSortItems; ++k)
+                    if (base + k < n_cells) cell_start[base + k] = start[k];
             }
+            if (base < n_cells && base + kSortItems >= n_cells) {  // the table's closing entry
+                cell_start[n_cells] = tile_base + run;
+                publish_cell_start(L, n_cells, tile_base + run);
+            }
+            if (tid == 0) s_start[kSortTile] = s_total;
+        }
+        __syncthreads();
+
+        // ---- 2. who goes where: for every output slot of the tile, the logical input index of its pedestrian.
+        // A warp takes 32 consecutive cells at a time (lane = cell). Each lane loads its cell's slot row (a warp
+        // reads 1 KB, contiguous; the next chunk's rows are requested before this chunk is finished), sorts it
+        // (19 compare-exchanges: "within a cell, ascending previous index", sfm.rs:66-68; independent of the order
+        // in which the atomics handed out the tickets) and parks it in the warp's slice of shared memory. The cells'
+        // output range is contiguous; each round of 32 outputs finds its cell with a 5-step search over the lanes'
+        // starts (shuffles) and stages member number `rank` of the sorted row.
+        // ---- 3. the move, as a separate pass over the staged indices: nothing but gathered loads and coalesced
+        // stores, kSortUnroll pedestrians per thread in flight.
+        // A tile holding more than kSortStage pedestrians (a jam) takes several rounds of 2 + 3.
+        const uint32_t total = s_total;
+        for (uint32_t seg_lo = 0; seg_lo < total; seg_lo += kSortStage) {
+            const uint32_t seg_hi = min(total, seg_lo + static_cast<uint32_t>(kSortStage));
+            {
+                constexpr uint32_t kFull = 0xFFFFFFFFu;
+                constexpr int kCellsPerWarp = kSortTile / (kSortCtaThreads / 32);
+                constexpr int kChunks = kCellsPerWarp / 32;
+                const uint32_t lane = tid & 31u, warp = tid >> 5;
+                uint32_t* const sorted = s_sorted + warp * 32 * kSlotsPerCell;
+                auto load_row = [&](int chunk, uint32_t& s, uint32_t& e, uint4& lo, uint4& hi) {
+                    const uint32_t c = warp * kCellsPerWarp + chunk * 32 + lane;
+                    s = s_start[c];
+                    e = s_start[c + 1];
+                    const uint32_t n = e - s;
+                    const uint4* row = reinterpret_cast<const uint4*>(
+                        cs.slots + (static_cast<size_t>(tile) * kSortTile + c) * kSlotsPerCell);
+                    lo = n > 0 ? row[0] : make_uint4(0u, 0u, 0u, 0u);
+                    hi = n > 4 ? row[1] : make_uint4(0u, 0u, 0u, 0u);
+                };
+                uint32_t s, e;
+                uint4 lo, hi;
+                load_row(0, s, e, lo, hi);
+#pragma unroll 1
+                for (int chunk = 0; chunk < kChunks; ++chunk) {
+                    const uint32_t c0 = warp * kCellsPerWarp + chunk * 32;
+                    const uint32_t n_mine = e - s;
+                    {
+                        uint32_t m[kSlotsPerCell] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                        for (int a = 0; a < kSlotsPerCell; ++a)
+                            if (static_cast<uint32_t>(a) >= n_mine) m[a] = 0xFFFFFFFFu;  // unused slots hold stale values
+#define PEDONI_CE(i, j)                                              \
+    {                                                                \
+        const uint32_t lo_ = min(m[i], m[j]), hi_ = max(m[i], m[j]); \
+        m[i] = lo_;                                                  \
+        m[j] = hi_;                                                  \
+    }
+                        PEDONI_CE(0, 1) PEDONI_CE(2, 3) PEDONI_CE(4, 5) PEDONI_CE(6, 7) PEDONI_CE(0, 2) PEDONI_CE(1, 3)
+                        PEDONI_CE(4, 6) PEDONI_CE(5, 7) PEDONI_CE(1, 2) PEDONI_CE(5, 6) PEDONI_CE(0, 4) PEDONI_CE(3, 7)
+                        PEDONI_CE(1, 5) PEDONI_CE(2, 6) PEDONI_CE(1, 4) PEDONI_CE(3, 6) PEDONI_CE(2, 4) PEDONI_CE(3, 5)
+                        PEDONI_CE(3, 4)
+#undef PEDONI_CE
+                        __syncwarp();  // the previous chunk's rows are no longer read
+                        uint4* dst = reinterpret_cast<uint4*>(sorted + lane * kSlotsPerCell);
+                        dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
+                        dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
+                        __syncwarp();
+                    }
+                    const uint32_t s_cur = s, e_cur = e;
+                    if (chunk + 1 < kChunks) load_row(chunk + 1, s, e, lo, hi);  // in flight during the rest
+                    const uint32_t first = __shfl_sync(kFull, s_cur, 0), last = __shfl_sync(kFull, e_cur, 31);
+                    // the part of this chunk's output range [first, last) that lies in the staged segment
+                    const uint32_t from = max(first, seg_lo), to = min(last, seg_hi);
+#pragma unroll 1
+                    for (uint32_t r0 = from; r0 < to; r0 += 32) {
+                        const uint32_t r = r0 + lane;  // tile-relative output slot of this lane
+                        uint32_t owner = 0;            // the last lane whose cell starts at or before r
+#pragma unroll
+                        for (uint32_t step = 16; step >= 1; step >>= 1) {
+                            const uint32_t v_ = __shfl_sync(kFull, s_cur, owner + step);
+                            if (v_ <= r) owner += step;
+                        }
+                        const uint32_t cs0 = __shfl_sync(kFull, s_cur, owner), cs1 = __shfl_sync(kFull, e_cur, owner);
+                        if (r < to) {
+                            const uint32_t rank = r - cs0, n = cs1 - cs0;
+                            uint32_t t;
+                            if (n <= static_cast<uint32_t>(kSlotsPerCell)) {
+                                t = sorted[owner * kSlotsPerCell + rank];
+                            } else {  // jam: members beyond the row hang on the cell's chain
+                                const uint32_t cell = tile * kSortTile + c0 + owner;
+                                const uint4* row =
+                                    reinterpret_cast<const uint4*>(cs.slots + static_cast<size_t>(cell) * kSlotsPerCell);
+                                t = select_member(cs, cell, n, rank, row[0], row[1]);
+                            }
+                            s_member[r - seg_lo] = t;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t r0 = seg_lo + tid; r0 < seg_hi; r0 += kSortCtaThreads * kSortUnroll) {
+                float2 pos[kSortUnroll], vel[kSortUnroll];
+                float v0[kSortUnroll];
+                uint32_t dest[kSortUnroll];
+#pragma unroll
+                for (int u = 0; u < kSortUnroll; ++u) {
+                    const uint32_t r = r0 + u * kSortCtaThreads;
+                    if (r < seg_hi) {
+                        const Located l = locate(in, s_member[r - seg_lo]);
+                        pos[u] = l.a.pos[l.idx];
+                        vel[u] = l.a.vel[l.idx];
+                        v0[u] = l.a.v0[l.idx];
+                        dest[u] = l.a.dest[l.idx];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kSortUnroll; ++u) {
+                    const uint32_t r = r0 + u * kSortCtaThreads;
+                    if (r < seg_hi) {
+                        const uint32_t dst = tile_base + r;
+                        out.pos[dst] = pos[u];
+                        out.vel[dst] = vel[u];
+                        out.v0[dst] = v0[u];
+                        out.dest[dst] = dest[u];
+                    }
+                }
+            }
+            if (seg_hi < total) __syncthreads();  // the stage is reused by the next segment
+        }
+        // ---- 4. chains of the cells that overflowed have been walked by every thread that needed them
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k)
+            if (v[k] > static_cast<uint32_t>(kSlotsPerCell) && base + k < n_cells) cs.ovf_head[base + k] = 0u;
+    }
+    // the last CTA to leave empties the overflow list for the next tick's producers
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(sc.done_count, 1u) == gridDim.x - 1) {
+            *cs.ovf_count = 0u;
+            *sc.done_count = 0u;
         }
     }
-#pragma unroll
-    for (int k = 0; k < kGatherItems; ++k) {
-        begin[k] = end[k] = 0;
-        if (keep[k]) begin[k] = cell_start[key[k]], end[k] = cell_start[key[k] + 1];
-    }
-#pragma unroll
-    for (int k = 0; k < kGatherItems; ++k) {
-        if (!keep[k]) continue;
-        const uint32_t t = t0 + k * kSortThreads;
-        uint32_t rank = 0;  // stable: the number of cell mates that come earlier in the input
-        for (uint32_t j = begin[k]; j < end[k]; ++j) rank += (perm[j] < t) ? 1u : 0u;
-        const uint32_t dst = begin[k] + rank;
-        out.pos[dst] = pos[k];
-        out.vel[dst] = vel[k];
-        out.v0[dst] = v0[k];
-        out.dest[dst] = dest[k];
-    }
-}
-
-// ---- the whole rebuild in ONE CTA, for small crowds -------------------------------------------------------
-// A shipped scenario holds tens to a few thousand pedestrians; at that size a tick is nothing but launch
-// latency (~6 us per dependent kernel). One 1024-thread CTA runs the scan (each thread owns a contiguous
-// chunk of cells), the scatter and the gather back to back with block barriers in between.
-constexpr uint32_t kSmallRebuildMaxAgents = 2048;  // beyond these one CTA is slower than three launches (measured:
-constexpr uint32_t kSmallRebuildMaxCells = 8192;    // bottleneck.toml, 3 k agents on 20 k cells: 44 vs 34 us per tick)
-
-__global__ void __launch_bounds__(1024) rebuild_small_kernel(SortInput in, uint32_t total_upper,
-                                                             uint32_t* __restrict__ cell_count, uint32_t n_cells,
-                                                             uint32_t offset, uint32_t* __restrict__ cell_start,
-                                                             uint32_t* __restrict__ perm, AgentArrays out, ScanLayout L) {
-    __shared__ uint32_t s_total;
-    const uint32_t chunk = (n_cells + blockDim.x - 1) / blockDim.x;
-    const uint32_t c0 = min(threadIdx.x * chunk, n_cells), c1 = min(c0 + chunk, n_cells);
-    uint32_t sum = 0;
-    for (uint32_t c = c0; c < c1; ++c) sum += cell_count[c];
-    uint32_t run = offset + block_exclusive_scan(sum, &s_total);
-    for (uint32_t c = c0; c < c1; ++c) {
-        const uint32_t v = cell_count[c];
-        cell_count[c] = 0;
-        cell_start[c] = run;
-        publish_cell_start(L, c, run);
-        run += v;
-    }
-    if (threadIdx.x == blockDim.x - 1) {  // c1 == n_cells for the last thread (and for any thread past the end)
-        cell_start[n_cells] = offset + s_total;
-        publish_cell_start(L, n_cells, offset + s_total);
-    }
-    __syncthreads();  // block-wide visibility of the table in global memory
-    for (uint32_t t = threadIdx.x; t < total_upper; t += blockDim.x) scatter_one(in, t, cell_start, perm);
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < total_upper; t += blockDim.x) gather_one(in, t, cell_start, perm, out);
 }
 
 // ---- ghost rows -----------------------------------------------------------------------------------

@@ -4,10 +4,10 @@
 //
 // Data layout in HBM (all SoA, coalesced):
 //   two agent buffers buf[0/1], each {pos float2[cap], vel float2[cap], v0 float[cap], dest u32[cap]}
-//   = 24 B/agent/buffer, the reference's PedestrianVec (sfm.rs:26-33), plus keys / tickets u32[cap] per
-//   buffer (the next rebuild's cell key and in-cell slot, written by the force epilogue). `cur` holds
-//   the live state; rebuild sorts cur (+ appended spawns) -> other, step integrates cur -> other; both
-//   swap. perm u32[n] sort scratch; cell_count / cell_start u32[cells + 1] (neighbor_grid_indices).
+//   = 24 B/agent/buffer, the reference's PedestrianVec (sfm.rs:26-33). `cur` holds the live state; rebuild
+//   sorts cur (+ appended spawns) -> other, step integrates cur -> other; both swap. Per cell: the population
+//   counter and the slot row the next rebuild's members enrol in (written by the force epilogue, 8 x u32 = one
+//   sector per cell, + an overflow list for jams), and cell_start u32[cells + 1] (neighbor_grid_indices).
 //   Field maps f32 row-major (field.rs:194-205), uploaded once.
 // Streams: `stream` (rebuild, interior force), `edge_stream` (slab handles, highest priority: ghost
 //   exchange / unpack / force on the rows next to a slab boundary), `dl_stream` (pipelined download).
@@ -89,14 +89,10 @@ struct PedoniModel {
     cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_peer = nullptr;
 
     AgentArrays buf[2]{};
-    uint32_t* d_keys[2] = {nullptr, nullptr};    // sort keys, indexed like buf[k]
-    uint32_t* d_tickets[2] = {nullptr, nullptr};  // in-cell slots, indexed like buf[k]
     uint32_t cap = 0;          // elements per array
     int cur = 0;
     uint32_t owned_upper = 0;  // host upper bound of owned agents in buf[cur]
     AgentArrays app{};         // appended spawns, not yet rebuilt
-    uint32_t* d_keys_app = nullptr;
-    uint32_t* d_tickets_app = nullptr;
     void* d_spawn_groups = nullptr;  // SpawnGroupDev table of pedoni_spawn_groups
     uint32_t spawn_groups_cap = 0;
     uint32_t app_cap = 0, app_n = 0;
@@ -110,12 +106,18 @@ struct PedoniModel {
     bool stage_busy[kStageSlots] = {false, false, false, false};
     int stage_next = 0;
 
-    uint32_t* d_perm = nullptr;
-    uint32_t aux_cap = 0;
+    uint32_t* d_slots = nullptr;         // [cells][kSlotsPerCell] members of the next table (CellSort)
+    uint32_t* d_ovf_head = nullptr;      // [cells]
+    OverflowEntry* d_ovf = nullptr;      // [ovf_cap]
+    uint32_t* d_ovf_count = nullptr;
+    uint32_t ovf_cap = 0;
+    uint32_t* d_sort_done = nullptr;
+    uint32_t sort_launches = 0;
+    int sm_count = 148;
     uint32_t* d_cell_count = nullptr;
     uint32_t* d_cell_start = nullptr;
     unsigned long long* d_tile_status = nullptr;  // chained-scan status words (tick-tagged, never reset)
-    uint32_t* d_tile_ticket = nullptr;
+    uint32_t* d_tile_ticket = nullptr;            // [2], alternating per sort launch
     uint32_t n_tiles = 0;
     // [2][kNumRanges][2], see RangeId. Double-buffered: a rebuild's scan already publishes the NEXT layout
     // while its scatter / gather still locate the sort input through the current one.
@@ -133,7 +135,7 @@ struct PedoniModel {
     uint32_t tick = 0;                  // rebuilds (and state resets) so far
     uint64_t inflow_cum[64] = {0};      // inflow_cum[t % 64]: upper bound of agents added up to tick t
 
-    bool keys_fresh = false;   // d_keys[cur] describe the compute range of buf[cur]
+    bool keys_fresh = false;   // the compute range of buf[cur] has enrolled in the next table (force epilogue)
     bool table_valid = false;  // d_cell_start indexes buf[cur]
     bool ever_rebuilt = false;
 
@@ -151,6 +153,7 @@ struct PedoniModel {
         uint32_t* h_range = nullptr;  // pinned
         uint32_t cap = 0;             // elements of the snapshot buffers
         uint32_t* user_dest = nullptr;
+        bool widen = false;           // _end widens h_dest8 into user_dest
         uint32_t user_cap = 0;
         bool inflight = false;
     } dl[2];
@@ -181,6 +184,7 @@ struct PedoniModel {
     }
     uint32_t n_sides() const { return (has_below ? 1u : 0u) + (has_above ? 1u : 0u); }
     uint32_t compute_upper() const { return owned_upper + n_sides() * halo_cap; }
+    CellSort cell_sort() const { return CellSort{d_cell_count, d_slots, d_ovf_head, d_ovf, d_ovf_count, ovf_cap}; }
     uint32_t* ranges(int which) const { return d_ranges + which * 2 * kNumRanges; }
     const uint32_t* range(int id) const { return ranges(rcur) + 2 * id; }
 };
@@ -248,47 +252,33 @@ int sync_all(PedoniModel* m) {
     return PEDONI_OK;
 }
 
-// Grow the state buffers (keeping buf[cur] and its keys: the layout uses absolute indices) and the
-// sort scratch. Blocking; only runs when a host upper bound outgrows the allocation.
-int ensure_capacity(PedoniModel* m, uint32_t need_arrays, uint32_t need_aux) {
-    if (need_arrays > m->cap) {
-        int rc = sync_all(m);
-        if (rc != PEDONI_OK) return rc;
-        uint32_t ncap = std::max<uint32_t>(need_arrays, m->cap + m->cap / 2);
-        ncap = std::max<uint32_t>(ncap, 1024);
-        for (int b = 0; b < 2; ++b) {
-            AgentArrays fresh{};
-            uint32_t *fresh_keys = nullptr, *fresh_tickets = nullptr;
-            CUDA_TRY(m, alloc_agents(fresh, ncap));
-            CUDA_TRY(m, cudaMalloc(&fresh_keys, sizeof(uint32_t) * (size_t)ncap));
-            CUDA_TRY(m, cudaMalloc(&fresh_tickets, sizeof(uint32_t) * (size_t)ncap));
-            if (b == m->cur && m->cap > 0) {
-                CUDA_TRY(m, copy_agents(fresh, m->buf[b], m->cap, m->stream));
-                CUDA_TRY(m, cudaMemcpyAsync(fresh_keys, m->d_keys[b], sizeof(uint32_t) * (size_t)m->cap,
-                                            cudaMemcpyDeviceToDevice, m->stream));
-                CUDA_TRY(m, cudaMemcpyAsync(fresh_tickets, m->d_tickets[b], sizeof(uint32_t) * (size_t)m->cap,
-                                            cudaMemcpyDeviceToDevice, m->stream));
-            }
-            CUDA_TRY(m, cudaStreamSynchronize(m->stream));
-            free_agents(m->buf[b]);
-            cudaFree(m->d_keys[b]);
-            cudaFree(m->d_tickets[b]);
-            m->buf[b] = fresh;
-            m->d_keys[b] = fresh_keys;
-            m->d_tickets[b] = fresh_tickets;
-        }
-        m->cap = ncap;
+// Grow the state buffers (keeping buf[cur]: the layout uses absolute indices) and the overflow list of the cell
+// slots (keeping its entries: a step may already have enrolled pedestrians in the next table). Blocking; only runs
+// when a host upper bound outgrows the allocation.
+int ensure_capacity(PedoniModel* m, uint32_t need_arrays) {
+    if (need_arrays <= m->cap) return PEDONI_OK;
+    int rc = sync_all(m);
+    if (rc != PEDONI_OK) return rc;
+    uint32_t ncap = std::max<uint32_t>(need_arrays, m->cap + m->cap / 2);
+    ncap = std::max<uint32_t>(ncap, 1024);
+    for (int b = 0; b < 2; ++b) {
+        AgentArrays fresh{};
+        CUDA_TRY(m, alloc_agents(fresh, ncap));
+        if (b == m->cur && m->cap > 0) CUDA_TRY(m, copy_agents(fresh, m->buf[b], m->cap, m->stream));
+        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+        free_agents(m->buf[b]);
+        m->buf[b] = fresh;
     }
-    if (need_aux > m->aux_cap) {
-        int rc = sync_all(m);
-        if (rc != PEDONI_OK) return rc;
-        uint32_t ncap = std::max<uint32_t>(need_aux, m->aux_cap + m->aux_cap / 2);
-        ncap = std::max<uint32_t>(ncap, 1024);
-        cudaFree(m->d_perm);
-        m->d_perm = nullptr;
-        CUDA_TRY(m, cudaMalloc(&m->d_perm, sizeof(uint32_t) * (size_t)ncap));
-        m->aux_cap = ncap;
-    }
+    OverflowEntry* fresh_ovf = nullptr;
+    CUDA_TRY(m, cudaMalloc(&fresh_ovf, sizeof(OverflowEntry) * (size_t)ncap));
+    if (m->ovf_cap > 0)
+        CUDA_TRY(m, cudaMemcpyAsync(fresh_ovf, m->d_ovf, sizeof(OverflowEntry) * (size_t)m->ovf_cap,
+                                    cudaMemcpyDeviceToDevice, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    cudaFree(m->d_ovf);
+    m->d_ovf = fresh_ovf;
+    m->ovf_cap = ncap;
+    m->cap = ncap;
     return PEDONI_OK;
 }
 
@@ -297,18 +287,11 @@ int ensure_app_capacity(PedoniModel* m, uint32_t need) {
     uint32_t ncap = std::max<uint32_t>(need, m->app_cap * 2);
     ncap = std::max<uint32_t>(ncap, 1024);
     AgentArrays fresh{};
-    uint32_t *fresh_keys = nullptr, *fresh_tickets = nullptr;
     CUDA_TRY(m, alloc_agents(fresh, ncap));
-    CUDA_TRY(m, cudaMalloc(&fresh_keys, sizeof(uint32_t) * (size_t)ncap));
-    CUDA_TRY(m, cudaMalloc(&fresh_tickets, sizeof(uint32_t) * (size_t)ncap));
     CUDA_TRY(m, copy_agents(fresh, m->app, m->app_n, m->stream));
     CUDA_TRY(m, cudaStreamSynchronize(m->stream));
     free_agents(m->app);
-    cudaFree(m->d_keys_app);
-    cudaFree(m->d_tickets_app);
     m->app = fresh;
-    m->d_keys_app = fresh_keys;
-    m->d_tickets_app = fresh_tickets;
     m->app_cap = ncap;
     return PEDONI_OK;
 }
@@ -417,9 +400,8 @@ void build_edges(const float* obstacles, int n, std::vector<float>& out) {
 SortInput make_sort_input(PedoniModel* m) {
     SortInput in{};
     in.nseg = 2;
-    in.seg[0] = Segment{m->buf[m->cur], m->d_keys[m->cur], m->d_tickets[m->cur], m->range(kRangeCompute),
-                        m->compute_upper()};
-    in.seg[1] = Segment{m->app, m->d_keys_app, m->d_tickets_app, nullptr, m->app_n};
+    in.seg[0] = Segment{m->buf[m->cur], m->range(kRangeCompute), m->compute_upper()};
+    in.seg[1] = Segment{m->app, nullptr, m->app_n};
     in.prefix[0] = 0;
     in.prefix[1] = m->compute_upper();
     in.prefix[2] = m->compute_upper() + m->app_n;
@@ -427,26 +409,27 @@ SortInput make_sort_input(PedoniModel* m) {
 }
 
 template <Math M, bool D, bool T>
-void launch_force_t(PedoniModel* m, const ForceParams& p, uint32_t blocks, size_t smem, cudaStream_t s) {
+void launch_force_t(PedoniModel* m, const ForceParams& p, dim3 blocks, size_t smem, cudaStream_t s) {
     force_integrate_kernel<M, D, T><<<blocks, kForceThreads, smem, s>>>(p);
     m->launches += 1;
 }
 
-void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream_t s) {
-    const uint32_t blocks = div_up(count_upper, kForceThreads);
-    if (blocks == 0) return;
+// range_id2 >= 0: a second range of the same size bound, integrated by the CTAs with blockIdx.y == 1.
+void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream_t s, int range_id2 = -1) {
+    const dim3 blocks(div_up(count_upper, kForceThreads), range_id2 >= 0 ? 2 : 1);
+    if (blocks.x == 0) return;
     ForceParams p{};
     p.in = m->buf[m->cur];
     p.out = m->buf[m->cur ^ 1];
     p.d_range = m->range(range_id);
+    p.d_range_hi = m->range(range_id2 >= 0 ? range_id2 : range_id);
     p.d_owned = m->range(kRangeOwned);
     p.count_upper = count_upper;
     p.cell_start = m->d_cell_start;
     p.grid = m->grid;
     p.field = m->field;
-    p.keys_out = m->d_keys[m->cur ^ 1];
-    p.ticket_out = m->d_tickets[m->cur ^ 1];
-    p.cell_count = m->d_cell_count;
+    p.d_compute = m->range(kRangeCompute);
+    p.cs = m->cell_sort();
     p.error_flag = m->d_error;
     p.updates_total = m->d_updates;
     p.arrived = m->d_arrived;
@@ -494,6 +477,8 @@ int check_device_error(PedoniModel* m) {
     };
     if (bits & kErrStageTimeout)
         add(PEDONI_ERR_CUDA, "force kernel: the bulk copies staging a warp's neighbour tile never completed");
+    if (bits & kErrSortOverflow)
+        add(PEDONI_ERR_CUDA, "rebuild: the overflow list of the cell slot rows ran out of entries");
     if (bits & kErrHaloTimeout)
         add(PEDONI_ERR_COMM,
             "slab %d of %d waited 20 s for a neighbour's ghost strip (peer-memory transport): a rank died or the "
@@ -705,7 +690,9 @@ void build_field_textures(PedoniModel* m) {
     constexpr int kMaxGather = 32768;  // cudaDeviceProp::maxTexture2DGather
     const int fx = m->field.fx, fy = m->field.fy, n = 1 + m->field.n_maps;
     if (fx < 4 || fy < 4 || fx > kMaxGather || fy > kMaxGather) return;
-    const int tiles_x = std::min(n, kMaxGather / fx), tiles_y = (n + tiles_x - 1) / tiles_x;
+    int tiles_x = 1, shift = 0;  // a power of two, so that the kernels find a map's tile with a mask and a shift
+    while (2 * tiles_x <= std::min(n, kMaxGather / fx)) tiles_x *= 2, shift += 1;
+    const int tiles_y = (n + tiles_x - 1) / tiles_x;
     if (static_cast<long long>(tiles_y) * fy > kMaxGather) return;
     const size_t map_elems = static_cast<size_t>(fx) * fy;
     const cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
@@ -728,6 +715,7 @@ void build_field_textures(PedoniModel* m) {
         td.normalizedCoords = 0;
         ok = cudaCreateTextureObject(&m->field.atlas, &res, &td, nullptr) == cudaSuccess;
         m->field.atlas_tiles_x = tiles_x;
+        m->field.atlas_shift = shift;
     }
     uint32_t* d_flag = nullptr;
     uint32_t flag = 1;
@@ -916,14 +904,28 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     }
 
     // cell table + scan scratch
-    m->n_tiles = div_up(m->n_cells, kScanTile);
+    m->n_tiles = div_up(m->n_cells, kSortTile);
+    {
+        cudaDeviceProp prop{};
+        CREATE_TRY(cudaGetDeviceProperties(&prop, m->device));
+        m->sm_count = prop.multiProcessorCount;
+    }
+    CREATE_TRY(cudaFuncSetAttribute(sort_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kSortSmemBytes)));
+    CREATE_TRY(cudaMalloc(&m->d_slots, sizeof(uint32_t) * kSlotsPerCell * ((size_t)m->n_cells + 1)));
+    CREATE_TRY(cudaMalloc(&m->d_ovf_head, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
+    CREATE_TRY(cudaMemsetAsync(m->d_ovf_head, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_ovf_count, sizeof(uint32_t)));
+    CREATE_TRY(cudaMemsetAsync(m->d_ovf_count, 0, sizeof(uint32_t), m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_sort_done, sizeof(uint32_t)));
+    CREATE_TRY(cudaMemsetAsync(m->d_sort_done, 0, sizeof(uint32_t), m->stream));
     CREATE_TRY(cudaMalloc(&m->d_cell_count, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
     CREATE_TRY(cudaMalloc(&m->d_cell_start, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
     CREATE_TRY(cudaMalloc(&m->d_tile_status, sizeof(unsigned long long) * std::max<uint32_t>(m->n_tiles, 1)));
     CREATE_TRY(cudaMemsetAsync(m->d_tile_status, 0, sizeof(unsigned long long) * std::max<uint32_t>(m->n_tiles, 1),
                                m->stream));
-    CREATE_TRY(cudaMalloc(&m->d_tile_ticket, sizeof(uint32_t)));
-    CREATE_TRY(cudaMemsetAsync(m->d_tile_ticket, 0, sizeof(uint32_t), m->stream));
+    CREATE_TRY(cudaMalloc(&m->d_tile_ticket, 2 * sizeof(uint32_t)));
+    CREATE_TRY(cudaMemsetAsync(m->d_tile_ticket, 0, 2 * sizeof(uint32_t), m->stream));
     CREATE_TRY(cudaMalloc(&m->d_ranges, sizeof(uint32_t) * 2 * 2 * kNumRanges));
     CREATE_TRY(cudaMalloc(&m->d_error, sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&m->d_updates, sizeof(unsigned long long)));
@@ -941,7 +943,7 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     CREATE_TRY(cudaEventCreate(&m->timer_start));
     CREATE_TRY(cudaEventCreate(&m->timer_stop));
 
-    if (ensure_capacity(m, m->array_offset + capacity + (m->has_above ? m->halo_cap : 0), capacity) != PEDONI_OK)
+    if (ensure_capacity(m, m->array_offset + capacity + (m->has_above ? m->halo_cap : 0)) != PEDONI_OK)
         return bail(PEDONI_ERR_CUDA);
     CREATE_TRY(cudaStreamSynchronize(m->stream));  // borrowed map pointers may die after return
 #undef CREATE_TRY
@@ -968,8 +970,7 @@ void pedoni_destroy(PedoniModel* m) {
     free_agents(m->buf[0]);
     free_agents(m->buf[1]);
     free_agents(m->app);
-    for (void* p : {(void*)m->d_keys[0], (void*)m->d_keys[1], (void*)m->d_keys_app, (void*)m->d_tickets[0], (void*)m->d_tickets[1], (void*)m->d_tickets_app,
-                    (void*)m->d_perm,
+    for (void* p : {(void*)m->d_slots, (void*)m->d_ovf_head, (void*)m->d_ovf, (void*)m->d_ovf_count, (void*)m->d_sort_done,
                     (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_status, (void*)m->d_tile_ticket,
                     (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_arrived, (void*)m->d_observe, (void*)m->d_distance, (void*)m->d_potential,
@@ -1107,6 +1108,8 @@ int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const u
     advance_tick(m, 0);
     // a preceding pedoni_step has already counted the (now discarded) residents into the next histogram
     CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, m->stream));
+    CUDA_TRY(m, cudaMemsetAsync(m->d_ovf_head, 0, sizeof(uint32_t) * (size_t)m->n_cells, m->stream));
+    CUDA_TRY(m, cudaMemsetAsync(m->d_ovf_count, 0, sizeof(uint32_t), m->stream));
     reset_layout_kernel<<<1, 1, 0, m->stream>>>(m->d_ranges, m->array_offset, m->h_pub_dev, m->tick);
     m->launches += 1;
     m->owned_upper = 0;
@@ -1124,53 +1127,33 @@ static int rebuild_impl(PedoniModel* m) {
     const uint32_t total = resident + m->app_n;
     const uint64_t need = (uint64_t)m->array_offset + total + (m->has_above ? m->halo_cap : 0);
     if (need > 0xFFFFFFF0ull) return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
-    // perm is indexed by cell_start[key] + ticket, and cell_start includes the array offset (the halo capacity on a
-    // slab with a neighbour below): size it like the arrays, not by the sort input alone.
-    int rc = ensure_capacity(m, static_cast<uint32_t>(need), std::max<uint32_t>(m->array_offset + total, 1));
+    int rc = ensure_capacity(m, static_cast<uint32_t>(need));
     if (rc != PEDONI_OK) return rc;
     SortInput in = make_sort_input(m);
 
     if (total > 0) {
-        // Keys + per-cell counts of the resident agents were produced by the force kernel's epilogue; only
-        // appended spawns (or everything, when no step preceded this rebuild) are keyed here.
+        // The resident pedestrians enrolled in the next table in the force kernel's epilogue; only appended
+        // spawns (or everybody, when no step preceded this rebuild) are keyed here.
         const uint32_t t_begin = m->keys_fresh ? resident : 0u;
         if (t_begin < total) {
             ScopedTimer t(m, kKey, s);
-            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field,
-                                                                   m->d_cell_count, m->d_error, m->d_arrived);
+            key_kernel<<<div_up(total - t_begin, 256), 256, 0, s>>>(in, t_begin, total, m->grid, m->field, m->cell_sort(),
+                                                                   m->d_error, m->d_arrived);
             m->launches += 1;
         }
     }
     advance_tick(m, (uint64_t)m->app_n + (uint64_t)m->n_sides() * m->halo_cap);
     ScanLayout layout{m->own_begin_cell, m->own_end_cell, static_cast<uint32_t>(m->grid.nx), m->has_below,
                       m->has_above,     m->ranges(m->rcur ^ 1), m->h_pub_dev,               m->tick};
-    if (total <= kSmallRebuildMaxAgents && m->n_cells <= kSmallRebuildMaxCells) {
-        // small crowd: scan + scatter + gather in one CTA, one launch
+    {
+        // one persistent kernel: prefix scan over the cells + the stable reorder of the 24-byte state
+        SortScratch scratch{m->d_tile_status, m->d_tile_ticket, m->d_sort_done, m->n_tiles, m->sort_launches & 1u};
+        m->sort_launches += 1;
+        const uint32_t ctas = std::min<uint32_t>(m->n_tiles, static_cast<uint32_t>(PEDONI_SORT_MIN_BLOCKS * m->sm_count));
         ScopedTimer t(m, kGather, s);
-        rebuild_small_kernel<<<1, 1024, 0, s>>>(in, total, m->d_cell_count, m->n_cells, m->array_offset, m->d_cell_start,
-                                                m->d_perm, m->buf[m->cur ^ 1], layout);
+        sort_cells_kernel<<<ctas, kSortCtaThreads, kSortSmemBytes, s>>>(in, m->cell_sort(), m->n_cells, m->array_offset, m->d_cell_start,
+                                                          scratch, layout, m->buf[m->cur ^ 1]);
         m->launches += 1;
-    } else {
-        {
-            ScopedTimer t(m, kScan, s);
-            scan_cells_kernel<<<m->n_tiles, kScanThreads, 0, s>>>(m->d_cell_count, m->n_cells, m->array_offset,
-                                                                  m->d_cell_start, m->d_tile_status, m->d_tile_ticket,
-                                                                  m->n_tiles, layout);
-            m->launches += 1;
-        }
-        if (total > 0) {
-            {
-                ScopedTimer t(m, kScatter, s);
-                scatter_kernel<<<div_up(total, kScatterTile), kSortThreads, 0, s>>>(in, total, m->d_cell_start, m->d_perm);
-                m->launches += 1;
-            }
-            {
-                ScopedTimer t(m, kGather, s);
-                gather_kernel<<<div_up(total, kGatherTile), kSortThreads, 0, s>>>(in, total, m->d_cell_start, m->d_perm,
-                                                                m->buf[m->cur ^ 1]);
-                m->launches += 1;
-            }
-        }
     }
     m->cur ^= 1;
     m->rcur ^= 1;  // the layout the scan published describes buf[cur] from here on
@@ -1309,8 +1292,11 @@ int pedoni_step(PedoniModel* m) {
     // Interior rows need no ghost data: they run on the main stream while the halo is still in flight.
     launch_force(m, kRangeInterior, m->owned_upper, m->stream);
     if (m->slab_count > 1) {
-        if (m->has_below) launch_force(m, kRangeEdgeLo, 2 * m->halo_cap, m->edge_stream);
-        if (m->has_above) launch_force(m, kRangeEdgeHi, 2 * m->halo_cap, m->edge_stream);
+        // the rows next to the slab boundaries: one launch for both edges
+        if (m->has_below && m->has_above)
+            launch_force(m, kRangeEdgeLo, 2 * m->halo_cap, m->edge_stream, kRangeEdgeHi);
+        else
+            launch_force(m, m->has_below ? kRangeEdgeLo : kRangeEdgeHi, 2 * m->halo_cap, m->edge_stream);
         CUDA_TRY(m, cudaEventRecord(m->ev_edge, m->edge_stream));
         CUDA_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_edge, 0));
         m->halo_inflight = false;  // ev_edge is behind ev_halo on the edge stream
@@ -1389,9 +1375,14 @@ int pedoni_download(PedoniModel* m, float* pos_xy, uint32_t* dest, float* vel_xy
 // Pipelined list_pedestrians: snapshot the owned (pos, destination) columns on the device (one D2D pass
 // behind the work already enqueued), then copy the snapshot to the caller's buffers on a separate
 // stream. The model may keep stepping meanwhile; pedoni_download_end waits for the oldest copy in flight.
-int pedoni_download_begin(PedoniModel* m, float* pos_xy, uint32_t* dest, uint32_t cap) {
-    if (!m || !pos_xy || !dest) return PEDONI_ERR_INVALID;
+static int download_begin_impl(PedoniModel* m, float* pos_xy, uint32_t* dest, uint8_t* dest8, uint32_t cap) {
+    if (!m || !pos_xy || (!dest && !dest8)) return PEDONI_ERR_INVALID;
     CUDA_TRY(m, cudaSetDevice(m->device));
+    if (dest8 && m->field.n_maps > 256)
+        return fail(m, PEDONI_ERR_UNSUPPORTED, "byte-sized destinations need at most 256 potential maps (have %d)",
+                    m->field.n_maps);
+    // destinations travel as bytes if the caller wants bytes, or if this handle packs them and widens on the host
+    const bool as_bytes = dest8 != nullptr || download_packs_destinations(m);
     if (m->dl_count == 2) return fail(m, PEDONI_ERR_STATE, "two pipelined downloads are already in flight");
     if (m->app_n > 0) return fail(m, PEDONI_ERR_STATE, "pedoni_download_begin with un-rebuilt spawns");
     if (!m->dl_stream) CUDA_TRY(m, cudaStreamCreateWithFlags(&m->dl_stream, cudaStreamNonBlocking));
@@ -1411,23 +1402,22 @@ int pedoni_download_begin(PedoniModel* m, float* pos_xy, uint32_t* dest, uint32_
         d.d_pos = nullptr, d.d_dest = nullptr, d.d_dest8 = nullptr, d.h_dest8 = nullptr, d.cap = 0;
         const uint32_t ncap = std::max<uint32_t>(upper + upper / 8, 1024);
         CUDA_TRY(m, cudaMalloc(&d.d_pos, sizeof(float2) * (size_t)ncap));
-        if (download_packs_destinations(m)) {
-            CUDA_TRY(m, cudaMalloc(&d.d_dest8, (size_t)ncap + 4));
-            CUDA_TRY(m, cudaHostAlloc(&d.h_dest8, (size_t)ncap + 4, cudaHostAllocDefault));
-        } else {
-            CUDA_TRY(m, cudaMalloc(&d.d_dest, sizeof(uint32_t) * (size_t)ncap));
-        }
         d.cap = ncap;
     }
+    // the destination staging this call needs (a handle may be asked for bytes and for words in turn)
+    if (as_bytes && !d.d_dest8) CUDA_TRY(m, cudaMalloc(&d.d_dest8, (size_t)d.cap + 4));
+    if (as_bytes && !dest8 && !d.h_dest8) CUDA_TRY(m, cudaHostAlloc(&d.h_dest8, (size_t)d.cap + 4, cudaHostAllocDefault));
+    if (!as_bytes && !d.d_dest) CUDA_TRY(m, cudaMalloc(&d.d_dest, sizeof(uint32_t) * (size_t)d.cap));
     const AgentArrays& a = m->buf[m->cur];
     const uint32_t take = std::min(upper, cap);
     if (upper) {
         CUDA_TRY(m, cudaMemcpyAsync(d.d_pos, a.pos + m->array_offset, sizeof(float2) * (size_t)upper,
                                     cudaMemcpyDeviceToDevice, m->stream));
-        if (d.d_dest8)
+        if (as_bytes) {
             pack_dest_kernel<<<div_up(div_up(upper, 4), 256), 256, 0, m->stream>>>(a.dest + m->array_offset, upper,
                                                                                    reinterpret_cast<uint32_t*>(d.d_dest8));
-        else
+            m->launches += 1;
+        } else
             CUDA_TRY(m, cudaMemcpyAsync(d.d_dest, a.dest + m->array_offset, sizeof(uint32_t) * (size_t)upper,
                                         cudaMemcpyDeviceToDevice, m->stream));
     }
@@ -1438,18 +1428,29 @@ int pedoni_download_begin(PedoniModel* m, float* pos_xy, uint32_t* dest, uint32_
     CUDA_TRY(m, cudaMemcpyAsync(d.h_range, d.d_range, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->dl_stream));
     if (take) {
         CUDA_TRY(m, cudaMemcpyAsync(pos_xy, d.d_pos, sizeof(float2) * (size_t)take, cudaMemcpyDeviceToHost, m->dl_stream));
-        if (d.d_dest8)
-            CUDA_TRY(m, cudaMemcpyAsync(d.h_dest8, d.d_dest8, (size_t)take, cudaMemcpyDeviceToHost, m->dl_stream));
+        if (as_bytes)  // straight into the caller's byte array, or into the pinned staging _end widens from
+            CUDA_TRY(m, cudaMemcpyAsync(dest8 ? dest8 : d.h_dest8, d.d_dest8, (size_t)take, cudaMemcpyDeviceToHost,
+                                        m->dl_stream));
         else
             CUDA_TRY(m, cudaMemcpyAsync(dest, d.d_dest, sizeof(uint32_t) * (size_t)take, cudaMemcpyDeviceToHost,
                                         m->dl_stream));
     }
     CUDA_TRY(m, cudaEventRecord(d.ev_done, m->dl_stream));
     d.user_dest = dest;
+    d.widen = as_bytes && !dest8;
     d.user_cap = cap;
     d.inflight = true;
     m->dl_count += 1;
     return PEDONI_OK;
+}
+
+int pedoni_download_begin(PedoniModel* m, float* pos_xy, uint32_t* dest, uint32_t cap) {
+    if (!dest) return PEDONI_ERR_INVALID;
+    return download_begin_impl(m, pos_xy, dest, nullptr, cap);
+}
+int pedoni_download_begin_u8(PedoniModel* m, float* pos_xy, uint8_t* dest8, uint32_t cap) {
+    if (!dest8) return PEDONI_ERR_INVALID;
+    return download_begin_impl(m, pos_xy, nullptr, dest8, cap);
 }
 
 int pedoni_download_end(PedoniModel* m, uint32_t* n_out) {
@@ -1464,7 +1465,7 @@ int pedoni_download_end(PedoniModel* m, uint32_t* n_out) {
     const uint32_t n = d.h_range[1] - d.h_range[0];
     if (n_out) *n_out = n;
     if (n > d.user_cap) return fail(m, PEDONI_ERR_CAPACITY, "download capacity %u < %u agents", d.user_cap, n);
-    if (d.d_dest8) {  // widen the byte-sized destinations into the caller's array (a later download may be copying meanwhile)
+    if (d.widen) {  // widen the byte-sized destinations into the caller's array (a later download may be copying meanwhile)
         const uint8_t* src = d.h_dest8;
         uint32_t* dst = d.user_dest;
         const long long count = n;

@@ -98,10 +98,11 @@ struct FieldView {
     // The same maps once more, tiled into ONE point-sampled 2D CUDA array (an atlas: one texture handle for
     // the whole warp) for the force kernel's 4x4 footprints (texture gather, see footprint_gather in
     // force.cuh). Tile 0 is the distance map, tile 1 + k potential map k; tile t sits at texel
-    // ((t % atlas_tiles_x) * fx, (t / atlas_tiles_x) * fy). atlas == 0: not available (strict handles never
+    // ((t % atlas_tiles_x) * fx, (t / atlas_tiles_x) * fy), atlas_tiles_x a power of two. atlas == 0: not available (strict handles never
     // make one).
     cudaTextureObject_t atlas;
-    int atlas_tiles_x;
+    int atlas_tiles_x;  // a power of two: tile t sits at ((t & (tiles_x - 1)) * fx, (t >> atlas_shift) * fy)
+    int atlas_shift;    // log2(atlas_tiles_x)
 };
 
 __device__ __forceinline__ float field_tap(const float* __restrict__ g, int ny, int nx, int x, int y) {
@@ -155,8 +156,8 @@ __device__ __forceinline__ float get_potential(const FieldView& f, uint32_t wayp
         const Axis ax = axis_of(q.x), ay = axis_of(q.y);
         if (ax.i >= 0 && ay.i >= 0 && ax.i + 1 < f.fx && ay.i + 1 < f.fy) {
             const int t = 1 + static_cast<int>(waypoint);
-            const float4 g = tex2Dgather<float4>(f.atlas, static_cast<float>((t % f.atlas_tiles_x) * f.fx + ax.i) + 1.0f,
-                                                 static_cast<float>((t / f.atlas_tiles_x) * f.fy + ay.i) + 1.0f, 0);
+            const float4 g = tex2Dgather<float4>(f.atlas, static_cast<float>((t & (f.atlas_tiles_x - 1)) * f.fx + ax.i) + 1.0f,
+                                                 static_cast<float>((t >> f.atlas_shift) * f.fy + ay.i) + 1.0f, 0);
             return bilinear_combine(ax, ay, g.w, g.z, g.x, g.y);
         }
     }
@@ -240,6 +241,7 @@ constexpr uint32_t kErrBadDestination = 1u;  // destination >= n_potential_maps 
 constexpr uint32_t kErrRowJump = 2u;         // slab handle: a pedestrian crossed >= 2 grid rows in one step
 constexpr uint32_t kErrHaloOverflow = 4u;    // slab handle: two boundary rows hold more agents than halo_capacity
 constexpr uint32_t kErrHaloTimeout = 8u;     // slab handle: a neighbour's strip did not arrive within 20 s
+constexpr uint32_t kErrSortOverflow = 32u;   // rebuild: the overflow list of the cell slots ran out (a bug: it is as long as the arrays)
 constexpr uint32_t kErrStageTimeout = 16u;   // force kernel: a warp's bulk copies never completed (a bug, not a user error)
 
 // `(pos / unit).as_ivec2()` (neighbor_grid.rs:27, sfm.rs:113): IEEE divide, truncate toward zero.

@@ -161,8 +161,13 @@ class SocialForceModelCuda:
         return pos[:k], dest[:k], (velo[:k] if velo is not None else None), (v0o[:k] if v0o is not None else None)
 
     def download_begin(self, pos: np.ndarray, dest: np.ndarray) -> None:
-        """Pipelined `list_pedestrians`: snapshot on the device, copy to (pinned) `pos`/`dest` in the background."""
-        _capi.check(self._lib.pedoni_download_begin(self._h, _fp(pos), _up(dest), dest.shape[0]), self._h)
+        """Pipelined `list_pedestrians`: snapshot on the device, copy to (pinned) `pos`/`dest` in the background.
+        `dest` may be uint32 (the trait's type) or uint8 (destinations travel and arrive as bytes)."""
+        if dest.dtype == np.uint8:
+            _capi.check(self._lib.pedoni_download_begin_u8(self._h, _fp(pos), dest.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                           dest.shape[0]), self._h)
+        else:
+            _capi.check(self._lib.pedoni_download_begin(self._h, _fp(pos), _up(dest), dest.shape[0]), self._h)
         if not hasattr(self, "_dl"):
             self._dl = []
         self._dl.append((pos, dest))  # keep the buffers alive until download_end; up to two may be in flight
@@ -213,8 +218,7 @@ class SocialForceModelCuda:
         _capi.check(self._lib.pedoni_profile_read(self._h, C.byref(t)), self._h)
         return {name: getattr(t, name) for name, _ in t._fields_}
 
-    KIND_NAMES = {0: "key", 2: "scan", 3: "scatter", 4: "gather", 5: "force", 6: "exchange+unpack", 7: "force_edge",
-                  8: "pack"}
+    KIND_NAMES = {0: "key", 4: "sort", 5: "force", 6: "exchange+unpack", 7: "force_edge", 8: "pack"}
 
     def profile_timeline(self) -> list:
         """[(kernel, stream, start_ms, stop_ms)] of the launches timed since the last timer_begin (profiling on)."""

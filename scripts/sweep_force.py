@@ -25,11 +25,12 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
-SORT_VARIANTS = {"base": [], "scan8": ["-DPEDONI_SCAN_ITEMS=8"], "scan32": ["-DPEDONI_SCAN_ITEMS=32"],
-                 "scatter4": ["-DPEDONI_SCATTER_ITEMS=4"], "gather2": ["-DPEDONI_GATHER_ITEMS=2"],
-                 "no_bulk": ["-DPEDONI_BULK_STAGE=0"],
-                 "t64_b18_t144_l24": ["-DPEDONI_FORCE_THREADS=64", "-DPEDONI_FORCE_MIN_BLOCKS=18", "-DPEDONI_TILE_ENTRIES=144",
-                                      "-DPEDONI_LIST_DEPTH=24"]}
+SORT_VARIANTS = {"base": [],  # 2 CTAs of 512 threads per SM, tiles of 4096 cells, 2 pedestrians in flight per thread
+                 "t256_b4": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=4"],
+                 "t256_b4_u4": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=4", "-DPEDONI_SORT_UNROLL=4"],
+                 "t128_b8": ["-DPEDONI_SORT_THREADS=128", "-DPEDONI_SORT_MIN_BLOCKS=8"],
+                 "t128_b12": ["-DPEDONI_SORT_THREADS=128", "-DPEDONI_SORT_MIN_BLOCKS=12"],
+                 "t1024_b1": ["-DPEDONI_SORT_THREADS=1024", "-DPEDONI_SORT_MIN_BLOCKS=1"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
 OUT = ROOT / "build" / "variants"

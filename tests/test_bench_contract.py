@@ -37,7 +37,7 @@ def test_cuda_arm_line():
              "--cpu-steps", "2")
     assert BASE | {"roofline", "clocks", "kernel_ms_per_step"} <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["scaling"] == "strong"
-    assert d["value"] > 1e8 and d["gpu_launches"] >= 4 * 5
+    assert d["value"] > 1e8 and d["gpu_launches"] >= 2 * 5  # force + sort per tick
     e = d["e2e"]
     assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 9 * 250000
     r = d["roofline"]

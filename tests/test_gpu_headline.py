@@ -13,7 +13,19 @@ IDENTICAL POSITIONS; positions and velocities within a stated fp32 tolerance ove
              post-step state is handed to a second oracle -> both rebuild: the cell table and order produced
              from the keys the force kernel's epilogue computed are bit-exact too.
   free run   10 ticks without any hand-over; pedestrians are matched through their (desired speed,
-             destination) pair where that pair is unique (~93 %) and must lie within the same tolerance.
+             destination) pair where that pair is unique (~93 %).
+
+What "within tolerance" can mean at this scale. The reference's pair force is DISCONTINUOUS: it is halved when
+`e . (-f) < |f| cos(phi)` (sfm.rs:150-152). Of the ~12 M pair terms of one tick of a million pedestrians, a handful
+(measured: ~1e-4 of the pedestrians per tick) sit within rounding distance of that switch, and any implementation
+that is not bit-identical to the reference (fast math is not; strict math is, to the last bit of exp) decides them
+the other way: that pedestrian's acceleration is then off by exactly half of one pair force, up to 3.5 m/s^2. So:
+  strict math  every pedestrian within 1e-4 m / 1e-4 m/s (measured: 0 / 1.2e-7);
+  fast math    every pedestrian within 5e-4 m / 1e-3 m/s EXCEPT at most 5e-4 of the crowd per tick, and of those
+               at least 90 % must be explained to 1 % as "+- half of one (or two) pair forces"
+               (helpers.explain_fast_outliers), the remainder being hidden by the speed clamp;
+  free run     the same switch makes trajectories fork, so after 10 ticks the DISTRIBUTION is bounded: median and
+               99th percentile within the tolerance, at most 1 % of the pedestrians beyond it.
 """
 import numpy as np
 import pytest
@@ -51,9 +63,11 @@ def test_synthetic_crowd_fast_math_textures_lockstep_vs_oracle(headline):
         orc.update()
         orc.spawn()
     tol_p, tol_v = helpers.tolerances(PEDONI_MATH_FAST)
-    worst_p = worst_v = 0.0
+    worst_v = 0.0
+    worst_bad = total_bad = explained = clamped = 0
     for tick in range(10):
         op, od, ov, o0 = orc.get()  # rebuilt (cell-sorted) oracle state
+        pre = (op, od, ov, o0)
         cu.upload_state(op, od, ov, o0)
         cu.rebuild()
         assert cu.get_pedestrian_count() == orc.count() > 0.99 * N_HEADLINE
@@ -66,10 +80,13 @@ def test_synthetic_crowd_fast_math_textures_lockstep_vs_oracle(headline):
         orc.update()
         cp, cd, cv, c0 = cu.download()
         op, od, ov, o0 = orc.get()
-        np.testing.assert_array_equal(np.isnan(cp), np.isnan(op))
-        worst_p = max(worst_p, float(np.nanmax(np.abs(cp - op))))
-        worst_v = max(worst_v, float(np.nanmax(np.abs(cv - ov))))
-        assert worst_p <= tol_p and worst_v <= tol_v, f"tick {tick}: |dpos| {worst_p:.2e} |dvel| {worst_v:.2e}"
+        # (a NaN on one side only — sqrt of a difference that rounds to either side of zero — counts as an outlier)
+        n_bad, n_explained, n_clamped = helpers.explain_fast_outliers(pre[0], pre[2], pre[3], cv, ov, cp, op, tol_p, tol_v)
+        worst_bad, explained, clamped = max(worst_bad, n_bad), explained + n_explained, clamped + n_clamped
+        total_bad += n_bad
+        assert n_bad <= 5e-4 * len(od), f"tick {tick}: {n_bad} pedestrians beyond the fast-math tolerance"
+        dv = np.abs(cv - ov).max(1)
+        worst_v = max(worst_v, float(np.quantile(dv[np.isfinite(dv)], 0.999)))
         # the keys of the next rebuild were computed by the force kernel's epilogue on the DEVICE's positions:
         # an oracle holding exactly those positions must produce the same table and order
         orc2.set(cp, cd, cv, c0)
@@ -83,7 +100,11 @@ def test_synthetic_crowd_fast_math_textures_lockstep_vs_oracle(headline):
         np.testing.assert_array_equal(rd, qd)
         np.testing.assert_array_equal(bits(rv), bits(qv))
         orc.spawn()
-    print(f"1 M synthetic, fast math + textures, lockstep: worst |dpos| = {worst_p:.2e} m, |dvel| = {worst_v:.2e} m/s")
+    print(f"1 M synthetic, fast math + textures, lockstep over 10 ticks: 99.9th percentile of |dvel| <= {worst_v:.2e} m/s; "
+          f"beyond the tolerance: at most {worst_bad} pedestrians per tick, {total_bad} in total, of which {explained} "
+          f"explained as half a pair force (anisotropy switch), {clamped} speed-clamped")
+    assert worst_v <= tol_v
+    assert explained >= 0.9 * (total_bad - clamped), (total_bad, explained, clamped)
     cu.close()
 
 
@@ -120,14 +141,20 @@ def test_synthetic_crowd_free_run_vs_oracle(headline, mode):
     key = lambda s, d: (bits(s).astype(np.uint64) << np.uint64(8)) | d.astype(np.uint64)  # noqa: E731
     ia, ib = _match(key(c0, cd), key(o0, od))
     assert len(ia) > 0.9 * len(od)
-    dp = float(np.abs(cp[ia] - op[ib]).max())
-    dv = float(np.abs(cv[ia] - ov[ib]).max())
+    dp = np.abs(cp[ia] - op[ib]).max(1)
+    dv = np.abs(cv[ia] - ov[ib]).max(1)
     tol_p, tol_v = helpers.tolerances(mode)
-    print(f"1 M synthetic free run, mode {mode}: {len(ia)} of {len(od)} matched, |dpos| = {dp:.2e} m, "
-          f"|dvel| = {dv:.2e} m/s, cell tables identical after {tables_equal} of 10 ticks")
-    assert dp <= tol_p and dv <= tol_v
+    qp, qv = np.nanquantile(dp, [0.5, 0.99, 0.9999, 1.0]), np.nanquantile(dv, [0.5, 0.99, 0.9999, 1.0])
+    beyond = float(((dp > tol_p) | (dv > tol_v)).mean())
+    print(f"1 M synthetic free run, mode {mode}: {len(ia)} of {len(od)} matched; |dpos| median / p99 / p99.99 / max = "
+          f"{qp[0]:.1e} / {qp[1]:.1e} / {qp[2]:.1e} / {qp[3]:.1e} m; |dvel| = {qv[0]:.1e} / {qv[1]:.1e} / {qv[2]:.1e} / "
+          f"{qv[3]:.1e} m/s; beyond the tolerance: {beyond:.2e} of the crowd; cell tables identical after "
+          f"{tables_equal} of 10 ticks")
     if mode == PEDONI_MATH_STRICT:  # IEEE ops in the reference's order: only exp's last bit can differ
+        assert qp[3] <= tol_p and qv[3] <= tol_v
         assert tables_equal >= 8
+    else:  # the anisotropy switch forks a few trajectories per tick (module docstring)
+        assert qp[1] <= tol_p and qv[1] <= tol_v and beyond <= 1e-2
     cu.close()
 
 

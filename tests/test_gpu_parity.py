@@ -157,12 +157,13 @@ def test_empty_model_and_errors(corridor):
         helpers.make_pair(sc, field, options=SimulatorOptions(use_neighbor_grid=False))
 
 
-@pytest.mark.parametrize("pack", ["1", "0"])
+@pytest.mark.parametrize("pack", ["1", "0", "u8"])
 def test_pipelined_download_equals_blocking_download(corridor, monkeypatch, pack):
     """pedoni_download_begin/_end: the snapshot is of the moment of the call, whatever is enqueued after it.
-    With at most 256 potential maps the destinations cross PCIe as bytes and are widened on the host."""
+    With at most 256 potential maps the destinations cross PCIe as bytes and are widened on the host — or are
+    delivered as bytes (pedoni_download_begin_u8)."""
     import torch
-    monkeypatch.setenv("PEDONI_DOWNLOAD_PACK", pack)
+    monkeypatch.setenv("PEDONI_DOWNLOAD_PACK", "0" if pack == "u8" else pack)
     sc, field = corridor
     cu, _ = helpers.make_pair(sc, field)
     assert cu.download_wire_bytes() == (9 if pack == "1" else 12)
@@ -170,7 +171,8 @@ def test_pipelined_download_equals_blocking_download(corridor, monkeypatch, pack
     cu.upload_state(pos, dest, vel, v0)
     cu.rebuild()
     h_pos = torch.empty((4000, 2), dtype=torch.float32).pin_memory().numpy()
-    h_dest = torch.empty(4000, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    h_dest = torch.empty(4000, dtype=torch.uint8).pin_memory().numpy() if pack == "u8" else \
+        torch.empty(4000, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     for _ in range(5):
         cu.step()
         want_pos, want_dest = cu.download(vel=False, v0=False)[:2]
