@@ -521,7 +521,7 @@ def run_ours(args):
             ("pack", "pack_ms"), ("exchange_unpack", "comm_ms"))}
         per_update, traffic_doc = traffic_record()
         use_traffic = per_update is not None and args.math == "fast" and args.density == 1.0 and \
-            args.agents == traffic_doc.get("agents_total")
+            abs(traffic_doc.get("agents_total", 0) - args.agents) <= 0.01 * args.agents  # captured at this workload
         compulsory = ALGO_BYTES_PER_UPDATE + map_bytes / args.agents
         out = {
             "metric": "pedestrian-updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
