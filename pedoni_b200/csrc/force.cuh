@@ -92,7 +92,6 @@ struct ForceParams {
     const uint32_t* cell_start;  // local cell table (neighbor_grid_indices, sfm.rs:22)
     GridView grid;
     FieldView field;
-    const uint32_t* d_compute;   // device [begin, end) of the next rebuild's resident segment: logical index = id - begin
     CellSort cs;                 // the next rebuild's cell membership (the enrolment is fused here)
     uint32_t* error_flag;
     unsigned long long* updates_total;  // += owned agents of this launch (thread 0 of block 0)
@@ -714,8 +713,8 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     p.out.dest[id] = dest;
     // ghost-row agents are integrated twice (here and by their owner): only the owner counts an arrival
     const bool owned = id >= p.d_owned[0] && id < p.d_owned[1];
-    enroll(p.cs, sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned, kTex), id - p.d_compute[0],
-           p.error_flag);
+    // the logical index of a resident pedestrian in the next rebuild's input is its array index (see locate())
+    enroll(p.cs, sort_key(p.grid, p.field, pn, dest, p.error_flag, p.arrived, owned, kTex), id, p.error_flag);
     // Slab handles exchange two ghost rows per tick, which covers every move of less than one grid row
     // (1.4 m per 0.1 s); anything faster would silently vanish at a slab boundary, so flag it.
     if (p.grid.slab) {

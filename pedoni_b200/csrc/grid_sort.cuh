@@ -62,9 +62,12 @@ struct SortInput {
     int nseg;
 };
 
-// Logical input index t -> the segment's arrays and the element index; live = false if t is beyond the
-// segment's live range. Two segments, resolved with selects (no dynamic indexing of the kernel
-// parameter, which would force a local-memory copy).
+// Logical input index t -> the segment's arrays and the element index; live = false if t is outside the
+// segment's live range. Segment 0 (the resident pedestrians) is indexed by the ABSOLUTE array index, t = idx:
+// the force kernel's epilogue knows it without reading the layout ranges (on a slab handle the lower end of the
+// compute range is only written by the ghost unpack, which runs concurrently with the interior force launch).
+// Segment 1 (appended spawns) follows at prefix[1], a host bound above every resident index. Two segments,
+// resolved with selects (no dynamic indexing of the kernel parameter, which would force a local-memory copy).
 struct Located {
     AgentArrays a;
     uint32_t idx;
@@ -79,15 +82,13 @@ __device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
     r.a.vel = second ? in.seg[1].a.vel : in.seg[0].a.vel;
     r.a.v0 = second ? in.seg[1].a.v0 : in.seg[0].a.v0;
     r.a.dest = second ? in.seg[1].a.dest : in.seg[0].a.dest;
-    const uint32_t* d_range = second ? in.seg[1].d_range : in.seg[0].d_range;
-    // d_range == nullptr: the population is host-known, [0, upper) (appended spawns).
-    uint32_t begin = 0, end = second ? in.seg[1].upper : in.seg[0].upper;
-    if (d_range != nullptr) {
-        begin = d_range[0];
-        end = d_range[1];
+    if (second) {  // the population of the appended spawns is host-known: [0, upper)
+        r.idx = t - in.prefix[1];
+        r.live = r.idx < in.seg[1].upper;
+    } else {
+        r.idx = t;
+        r.live = t >= in.seg[0].d_range[0] && t < in.seg[0].d_range[1];
     }
-    r.idx = begin + (t - (second ? in.prefix[1] : in.prefix[0]));
-    r.live = r.idx < end;
     return r;
 }
 

@@ -184,6 +184,8 @@ struct PedoniModel {
     }
     uint32_t n_sides() const { return (has_below ? 1u : 0u) + (has_above ? 1u : 0u); }
     uint32_t compute_upper() const { return owned_upper + n_sides() * halo_cap; }
+    // host bound above the array index of every pedestrian this handle integrates (owned + the ghost row above)
+    uint32_t resident_hi() const { return array_offset + owned_upper + (has_above ? halo_cap : 0u); }
     CellSort cell_sort() const { return CellSort{d_cell_count, d_slots, d_ovf_head, d_ovf, d_ovf_count, ovf_cap}; }
     uint32_t* ranges(int which) const { return d_ranges + which * 2 * kNumRanges; }
     const uint32_t* range(int id) const { return ranges(rcur) + 2 * id; }
@@ -400,11 +402,12 @@ void build_edges(const float* obstacles, int n, std::vector<float>& out) {
 SortInput make_sort_input(PedoniModel* m) {
     SortInput in{};
     in.nseg = 2;
-    in.seg[0] = Segment{m->buf[m->cur], m->range(kRangeCompute), m->compute_upper()};
+    // segment 0 is addressed by absolute array index: everything below resident_hi() (see locate())
+    in.seg[0] = Segment{m->buf[m->cur], m->range(kRangeCompute), m->resident_hi()};
     in.seg[1] = Segment{m->app, nullptr, m->app_n};
     in.prefix[0] = 0;
-    in.prefix[1] = m->compute_upper();
-    in.prefix[2] = m->compute_upper() + m->app_n;
+    in.prefix[1] = m->resident_hi();
+    in.prefix[2] = m->resident_hi() + m->app_n;
     return in;
 }
 
@@ -428,7 +431,6 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     p.cell_start = m->d_cell_start;
     p.grid = m->grid;
     p.field = m->field;
-    p.d_compute = m->range(kRangeCompute);
     p.cs = m->cell_sort();
     p.error_flag = m->d_error;
     p.updates_total = m->d_updates;
@@ -1123,9 +1125,10 @@ int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const u
 
 static int rebuild_impl(PedoniModel* m) {
     cudaStream_t s = m->stream;
-    const uint32_t resident = m->compute_upper();
+    const uint32_t resident = m->resident_hi();  // logical indices below this are array indices of buf[cur]
     const uint32_t total = resident + m->app_n;
-    const uint64_t need = (uint64_t)m->array_offset + total + (m->has_above ? m->halo_cap : 0);
+    // worst case every input pedestrian is kept, and the ghosts from above land right behind them
+    const uint64_t need = (uint64_t)m->array_offset + m->compute_upper() + m->app_n + (m->has_above ? m->halo_cap : 0);
     if (need > 0xFFFFFFF0ull) return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
     int rc = ensure_capacity(m, static_cast<uint32_t>(need));
     if (rc != PEDONI_OK) return rc;

@@ -30,7 +30,7 @@ def test_multi_gpu_slabs_equal_whole_domain(world, transport):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + (10 if transport == "nccl" else 0)),
            str(ROOT / "tests" / "nccl_slab_worker.py"), "400000", "25"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0 and "NCCL-SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     assert ("peer-memory" if transport == "peer" else "nccl send/recv") in r.stdout, r.stdout[-500:]
 
@@ -43,5 +43,5 @@ def test_multi_gpu_slabs_on_a_growing_scenario():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29640",
            str(ROOT / "tests" / "nccl_slab_worker.py"), "scenario:bottleneck", "400"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "NCCL-SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
