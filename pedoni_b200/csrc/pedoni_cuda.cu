@@ -86,7 +86,7 @@ struct PedoniModel {
     pedoni::SlabComm* comm = nullptr;
     bool halo_pending = false;   // rebuilt, ghosts not exchanged yet (in-process transport)
     bool halo_inflight = false;  // exchange enqueued on edge_stream, main has not waited on ev_halo
-    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_peer = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_peer = nullptr, ev_sorted = nullptr;
 
     AgentArrays buf[2]{};
     uint32_t cap = 0;          // elements per array
@@ -870,7 +870,7 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
         m->arena_bytes = PedoniModel::kArenaControlBytes + 4 * m->slot_bytes;
         CREATE_TRY(cudaMalloc(&m->d_arena, m->arena_bytes));
         CREATE_TRY(cudaMemsetAsync(m->d_arena, 0, m->arena_bytes, m->stream));
-        for (cudaEvent_t* e : {&m->ev_packed, &m->ev_halo, &m->ev_edge, &m->ev_peer})
+        for (cudaEvent_t* e : {&m->ev_packed, &m->ev_halo, &m->ev_edge, &m->ev_peer, &m->ev_sorted})
             CREATE_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
 
@@ -966,7 +966,7 @@ void pedoni_destroy(PedoniModel* m) {
         cudaEventDestroy(t.stop);
     }
     for (auto e : m->event_pool) cudaEventDestroy(e);
-    for (cudaEvent_t e : {m->timer_start, m->timer_stop, m->ev_packed, m->ev_halo, m->ev_edge, m->ev_peer})
+    for (cudaEvent_t e : {m->timer_start, m->timer_stop, m->ev_packed, m->ev_halo, m->ev_edge, m->ev_peer, m->ev_sorted})
         if (e) cudaEventDestroy(e);
     release_field_textures(m);
     free_agents(m->buf[0]);
@@ -1184,14 +1184,18 @@ static int rebuild_impl(PedoniModel* m) {
                 sig.flag_up = m->flag_below(m->peer_arena_above);
             }
         }
+        // Pack (and, with the peer-memory transport, send) on the EDGE stream, behind the sort: the main stream goes
+        // straight on to the interior force launch, which only reads what the pack reads.
+        CUDA_TRY(m, cudaEventRecord(m->ev_sorted, s));
+        CUDA_TRY(m, cudaStreamWaitEvent(m->edge_stream, m->ev_sorted, 0));
         {
-            ScopedTimer t(m, kPack, s);
-            halo_pack_kernel<<<grid, 256, 0, s>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell, m->own_end_cell,
-                                                  m->grid.nx, m->halo_cap, down, up, m->has_below, m->has_above,
-                                                  m->tick, m->d_error, sig);
+            ScopedTimer t(m, kPack, m->edge_stream);
+            halo_pack_kernel<<<grid, 256, 0, m->edge_stream>>>(m->buf[m->cur], m->d_cell_start, m->own_begin_cell,
+                                                              m->own_end_cell, m->grid.nx, m->halo_cap, down, up,
+                                                              m->has_below, m->has_above, m->tick, m->d_error, sig);
             m->launches += 1;
         }
-        CUDA_TRY(m, cudaEventRecord(m->ev_packed, s));
+        CUDA_TRY(m, cudaEventRecord(m->ev_packed, m->edge_stream));
         m->halo_pending = true;
         if (m->transport == PedoniModel::kTransportPeer)
             rc = exchange_peer(m);
