@@ -127,6 +127,10 @@ extern "C" {
     pub fn pedoni_field_build(size_x: f32, size_y: f32, unit: f32, n_obstacles: i32, obstacles: *const f32,
                               n_waypoints: i32, waypoints: *const f32, obstacle_exist: *mut u8,
                               distance_map: *mut f32, potential_maps: *mut f32) -> c_int;
+    pub fn pedoni_field_build_device(device: i32, size_x: f32, size_y: f32, unit: f32, n_obstacles: i32,
+                                     obstacles: *const f32, n_waypoints: i32, waypoints: *const f32,
+                                     obstacle_exist: *mut u8, distance_map: *mut f32, potential_maps: *mut f32,
+                                     passes_out: *mut i32) -> c_int;
     pub fn pedoni_field_textures(model: *const PedoniModel) -> c_int;
     pub fn pedoni_profile_enable(model: *mut PedoniModel, enable: i32) -> c_int;
     pub fn pedoni_profile_reset(model: *mut PedoniModel) -> c_int;

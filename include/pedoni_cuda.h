@@ -238,6 +238,18 @@ int pedoni_field_build(float size_x, float size_y, float unit, int32_t n_obstacl
                        int32_t n_waypoints, const float* waypoints, uint8_t* obstacle_exist, float* distance_map,
                        float* potential_maps);
 
+/* The same precompute ON THE GPU (second half), for domains where the serial heap
+ * marching takes minutes (the 10 M synthetic crowd: three maps of 12 656^2 cells). Same rasterised inputs, same
+ * per-cell upwind update (field.rs:177-187) and costs, solved as the fixed point of that update by a block-iterative
+ * scheme (32 x 32 tiles relaxed in shared memory, a changed edge wakes the neighbouring tile) instead of by marching.
+ * Equal to pedoni_field_build to rounding (<= 1e-3 field cells on every shipped scenario, most maps bit-identical:
+ * tests/test_gpu_field_device.py), not bit for bit: sums are formed in a different order. Outputs as for
+ * pedoni_field_build (host arrays); *passes_out = relaxation passes over the grid, summed over the maps. Needs a CUDA
+ * device (PEDONI_ERR_CUDA otherwise: the host builder is pedoni_field_build). */
+int pedoni_field_build_device(int32_t device, float size_x, float size_y, float unit, int32_t n_obstacles,
+                              const float* obstacles, int32_t n_waypoints, const float* waypoints,
+                              uint8_t* obstacle_exist, float* distance_map, float* potential_maps, int32_t* passes_out);
+
 /* ---- measurement (bench.py): device-side timers on the handle's own stream ---------------------- */
 
 typedef struct PedoniKernelTimes {

@@ -109,6 +109,8 @@ SIGNATURES = {
     "pedoni_field_shape": (C.c_int, [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pedoni_field_build": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_int32, c_float_p, C.c_int32, c_float_p,
                                      C.POINTER(C.c_uint8), c_float_p, c_float_p]),
+    "pedoni_field_build_device": (C.c_int, [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, c_float_p, C.c_int32,
+                                            c_float_p, C.POINTER(C.c_uint8), c_float_p, c_float_p, C.POINTER(C.c_int32)]),
     "pedoni_slab_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pedoni_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pedoni_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),

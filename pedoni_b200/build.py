@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False, out: Path | None = None, e
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     env = dict(os.environ)
-    subprocess.run(cmd, check=True, env=env)
+    subprocess.run(cmd, check=True, env=env, stdin=subprocess.DEVNULL, timeout=900)
     return out
 
 

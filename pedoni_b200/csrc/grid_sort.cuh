@@ -291,6 +291,7 @@ struct SortScratch {
     uint32_t* done_count;             // CTAs of this launch that have finished (the last one resets the overflow list)
     uint32_t n_tiles;
     uint32_t parity;
+    uint32_t items;  // cells per thread of this launch (1 .. kSortItems): a tile is kSortCtaThreads * items cells
 };
 
 // The member of `cell` with exactly `rank` smaller logical indices among its n members.
@@ -356,9 +357,10 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
         if (tile >= sc.n_tiles) break;
 
         // ---- 1. populations -> starts
-        const uint32_t base = tile * kSortTile + tid * kSortItems;
+        const uint32_t items = sc.items, tile_cells = kSortCtaThreads * items;
+        const uint32_t base = tile * tile_cells + tid * items;
         uint32_t v[kSortItems];
-        if (base + kSortItems <= n_cells) {
+        if (items == kSortItems && base + kSortItems <= n_cells) {
             uint4* p = reinterpret_cast<uint4*>(cs.cell_count + base);
 #pragma unroll
             for (int q = 0; q < kSortItems / 4; ++q) {
@@ -369,8 +371,9 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
         } else {
 #pragma unroll
             for (int k = 0; k < kSortItems; ++k) {
-                v[k] = (base + k < n_cells) ? cs.cell_count[base + k] : 0u;
-                if (base + k < n_cells) cs.cell_count[base + k] = 0u;
+                const bool mine = static_cast<uint32_t>(k) < items && base + k < n_cells;
+                v[k] = mine ? cs.cell_count[base + k] : 0u;
+                if (mine) cs.cell_count[base + k] = 0u;
             }
         }
         uint32_t sum = 0;
@@ -404,11 +407,13 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
 #pragma unroll
             for (int k = 0; k < kSortItems; ++k) {
                 start[k] = tile_base + run;
-                s_start[tid * kSortItems + k] = run;
-                if (base + k < n_cells) publish_cell_start(L, base + k, tile_base + run);
+                if (static_cast<uint32_t>(k) < items) {
+                    s_start[tid * items + k] = run;
+                    if (base + k < n_cells) publish_cell_start(L, base + k, tile_base + run);
+                }
                 run += v[k];
             }
-            if (base + kSortItems <= n_cells) {
+            if (items == kSortItems && base + kSortItems <= n_cells) {
                 // 16-byte stores: scalar ones reach L2 as one partial-sector write per cell
                 uint4* p = reinterpret_cast<uint4*>(cell_start + base);
 #pragma unroll
@@ -417,13 +422,13 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
             } else {
 #pragma unroll
                 for (int k = 0; k < kSortItems; ++k)
-                    if (base + k < n_cells) cell_start[base + k] = start[k];
+                    if (static_cast<uint32_t>(k) < items && base + k < n_cells) cell_start[base + k] = start[k];
             }
-            if (base < n_cells && base + kSortItems >= n_cells) {  // the table's closing entry
+            if (base < n_cells && base + items >= n_cells) {  // the table's closing entry
                 cell_start[n_cells] = tile_base + run;
                 publish_cell_start(L, n_cells, tile_base + run);
             }
-            if (tid == 0) s_start[kSortTile] = s_total;
+            if (tid == 0) s_start[tile_cells] = s_total;
         }
         __syncthreads();
 
@@ -442,8 +447,8 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
             const uint32_t seg_hi = min(total, seg_lo + static_cast<uint32_t>(kSortStage));
             {
                 constexpr uint32_t kFull = 0xFFFFFFFFu;
-                constexpr int kCellsPerWarp = kSortTile / (kSortCtaThreads / 32);
-                constexpr int kChunks = kCellsPerWarp / 32;
+                const uint32_t kCellsPerWarp = 32u * items;  // the cells of this warp's threads
+                const int kChunks = static_cast<int>(items);
                 const uint32_t lane = tid & 31u, warp = tid >> 5;
                 uint32_t* const sorted = s_sorted + warp * 32 * kSlotsPerCell;
                 auto load_row = [&](int chunk, uint32_t& s, uint32_t& e, uint4& lo, uint4& hi) {
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
                     e = s_start[c + 1];
                     const uint32_t n = e - s;
                     const uint4* row = reinterpret_cast<const uint4*>(
-                        cs.slots + (static_cast<size_t>(tile) * kSortTile + c) * kSlotsPerCell);
+                        cs.slots + (static_cast<size_t>(tile) * tile_cells + c) * kSlotsPerCell);
                     lo = n > 0 ? row[0] : make_uint4(0u, 0u, 0u, 0u);
                     hi = n > 4 ? row[1] : make_uint4(0u, 0u, 0u, 0u);
                 };
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
                             if (n <= static_cast<uint32_t>(kSlotsPerCell)) {
                                 t = sorted[owner * kSlotsPerCell + rank];
                             } else {  // jam: members beyond the row hang on the cell's chain
-                                const uint32_t cell = tile * kSortTile + c0 + owner;
+                                const uint32_t cell = tile * tile_cells + c0 + owner;
                                 const uint4* row =
                                     reinterpret_cast<const uint4*>(cs.slots + static_cast<size_t>(cell) * kSlotsPerCell);
                                 t = select_member(cs, cell, n, rank, row[0], row[1]);
@@ -550,7 +555,8 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k)
-            if (v[k] > static_cast<uint32_t>(kSlotsPerCell) && base + k < n_cells) cs.ovf_head[base + k] = 0u;
+            if (v[k] > static_cast<uint32_t>(kSlotsPerCell) && static_cast<uint32_t>(k) < items && base + k < n_cells)
+                cs.ovf_head[base + k] = 0u;
     }
     // the last CTA to leave empties the overflow list for the next tick's producers
     if (tid == 0) {

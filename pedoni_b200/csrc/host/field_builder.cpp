@@ -74,6 +74,13 @@ class FieldBuilder {
             std::copy(potentials_[k].begin(), potentials_[k].end(), potential_maps + static_cast<size_t>(k) * cells());
     }
 
+    // For the device builder (field_device.cu): the rasterised inputs of the marching, nothing marched.
+    const std::vector<uint8_t>& obstacle_mask() const { return obstacle_; }
+    // cells of a waypoint's outline (potential 0), as flat indices y * nx + x, without a full-size grid
+    void waypoint_outline_cells(const float* w, std::vector<uint32_t>& out) const {
+        outline(w, [&out, this](int x, int y) { out.push_back(static_cast<uint32_t>(at(x, y))); });
+    }
+
   private:
     float unit_;
     int nx_ = 0, ny_ = 0;
@@ -236,6 +243,22 @@ class FieldBuilder {
 };
 
 }  // namespace
+
+namespace pedoni {
+// Rasterisation only (field.rs:29-32,42-88): obstacle mask incl. the border ring, and per waypoint the cells of
+// its outline. Shared with the device builder so that both march from exactly the same inputs.
+int rasterize_scenario(float size_x, float size_y, float unit, int n_obstacles, const float* obstacles, int n_waypoints,
+                       const float* waypoints, std::vector<uint8_t>& obstacle_mask,
+                       std::vector<std::vector<uint32_t>>& waypoint_cells) {
+    FieldBuilder b(size_x, size_y, unit);
+    for (int k = 0; k < n_obstacles; ++k) b.add_obstacle(obstacles + 5 * k);
+    obstacle_mask = b.obstacle_mask();
+    waypoint_cells.clear();
+    waypoint_cells.resize(static_cast<size_t>(n_waypoints));
+    for (int k = 0; k < n_waypoints; ++k) b.waypoint_outline_cells(waypoints + 5 * k, waypoint_cells[k]);
+    return 0;
+}
+}  // namespace pedoni
 
 extern "C" {
 

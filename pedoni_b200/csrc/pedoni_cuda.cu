@@ -906,7 +906,7 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     }
 
     // cell table + scan scratch
-    m->n_tiles = div_up(m->n_cells, kSortTile);
+    m->n_tiles = div_up(m->n_cells, kSortCtaThreads);  // status words for the smallest tile (one cell per thread)
     {
         cudaDeviceProp prop{};
         CREATE_TRY(cudaGetDeviceProperties(&prop, m->device));
@@ -1150,9 +1150,14 @@ static int rebuild_impl(PedoniModel* m) {
                       m->has_above,     m->ranges(m->rcur ^ 1), m->h_pub_dev,               m->tick};
     {
         // one persistent kernel: prefix scan over the cells + the stable reorder of the 24-byte state
-        SortScratch scratch{m->d_tile_status, m->d_tile_ticket, m->d_sort_done, m->n_tiles, m->sort_launches & 1u};
+        // Cells per thread: as few as keep every resident CTA busy with one tile (a tile's latency grows with the
+        // cells a thread owns; a 10 M crowd on one GPU takes the full 8, a slab of an 8-GPU run 5).
+        const uint32_t slots = static_cast<uint32_t>(PEDONI_SORT_MIN_BLOCKS * m->sm_count);
+        const uint32_t items = std::min<uint32_t>(kSortItems, std::max<uint32_t>(1u, div_up(m->n_cells, slots * kSortCtaThreads)));
+        const uint32_t n_tiles = div_up(m->n_cells, items * kSortCtaThreads);
+        SortScratch scratch{m->d_tile_status, m->d_tile_ticket, m->d_sort_done, n_tiles, m->sort_launches & 1u, items};
         m->sort_launches += 1;
-        const uint32_t ctas = std::min<uint32_t>(m->n_tiles, static_cast<uint32_t>(PEDONI_SORT_MIN_BLOCKS * m->sm_count));
+        const uint32_t ctas = std::min<uint32_t>(n_tiles, slots);
         ScopedTimer t(m, kGather, s);
         sort_cells_kernel<<<ctas, kSortCtaThreads, kSortSmemBytes, s>>>(in, m->cell_sort(), m->n_cells, m->array_offset, m->d_cell_start,
                                                           scratch, layout, m->buf[m->cur ^ 1]);

@@ -23,8 +23,9 @@ class Field:
     potential_maps: np.ndarray   # f32 (n_waypoints, fy, fx), field.rs:204
 
     @staticmethod
-    def from_scenario(scenario, unit: float) -> "Field":
-        """field.rs:220-232. Host only: works without a GPU."""
+    def from_scenario(scenario, unit: float, device=None) -> "Field":
+        """field.rs:220-232. device=None: the host builder (the reference's marching restated, works without a GPU);
+        device=k: the block-iterative eikonal solver on GPU k (pedoni_field_build_device), for large domains."""
         from . import _capi
         lib = _capi.load()
         fy, fx = C.c_int32(), C.c_int32()
@@ -38,7 +39,15 @@ class Field:
         dist = np.zeros((fy, fx), np.float32)
         pots = np.zeros((len(wps), fy, fx), np.float32)
         fp = lambda a: a.ctypes.data_as(_capi.c_float_p)  # noqa: E731
-        _capi.check(lib.pedoni_field_build(sx, sy, unit, len(obs), fp(obs), len(wps), fp(wps),
-                                           exist.ctypes.data_as(C.POINTER(C.c_uint8)), fp(dist), fp(pots)))
+        if device is None:
+            _capi.check(lib.pedoni_field_build(sx, sy, unit, len(obs), fp(obs), len(wps), fp(wps),
+                                               exist.ctypes.data_as(C.POINTER(C.c_uint8)), fp(dist), fp(pots)))
+        else:
+            passes = C.c_int32()
+            rc = lib.pedoni_field_build_device(int(device), sx, sy, unit, len(obs), fp(obs), len(wps), fp(wps),
+                                               exist.ctypes.data_as(C.POINTER(C.c_uint8)), fp(dist), fp(pots),
+                                               C.byref(passes))
+            if rc < 0:
+                raise _capi.PedoniError(rc, "pedoni_field_build_device failed (needs a CUDA device; see stderr)")
         return Field(unit=unit, shape=(fy, fx), obstacle_exist=exist.astype(bool), distance_map=dist,
                      potential_maps=pots)

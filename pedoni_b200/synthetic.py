@@ -84,8 +84,12 @@ class SyntheticCrowd:
         vel = np.zeros((hi - lo, 2), np.float32)
         return pos, dest, vel, v0
 
-    def field(self) -> Field:
-        """Closed-form open-domain field (see module docstring)."""
+    def field(self, device=None) -> Field:
+        """device=k: the field of this scenario built on GPU k by pedoni_field_build_device (what bench.py feeds
+        the model). device=None: the closed-form open-domain field (see module docstring), for boxes without a
+        GPU and for small tests; it equals the built one up to the corner effects of the border ring."""
+        if device is not None:
+            return Field.from_scenario(self.scenario(), self.field_unit, device=device)
         h = np.float32(self.field_unit)
         s = np.float32(self.side)
         n = int(math.ceil(float(s / h)))  # field.rs:25-26
