@@ -62,6 +62,16 @@ pub struct PedoniObservables {
 }
 
 #[repr(C)]
+pub struct PedoniSpawnRate {
+    pub p1_x: f32,
+    pub p1_y: f32,
+    pub p2_x: f32,
+    pub p2_y: f32,
+    pub destination: u32,
+    pub frequency: f64,
+}
+
+#[repr(C)]
 pub struct PedoniKernelTimes {
     pub key_ms: f64,
     pub histogram_ms: f64,
@@ -113,6 +123,9 @@ extern "C" {
     // the whole header (tests/test_capi_symbols.py checks the names)
     pub fn pedoni_spawn_groups(model: *mut PedoniModel, n_groups: u32, groups: *const PedoniSpawnGroup, seed: u64,
                                counter: u64) -> c_int;
+    pub fn pedoni_spawn_stream_seek(model: *mut PedoniModel, seed: u64, counter: u64) -> c_int;
+    pub fn pedoni_spawn_stream_tell(model: *mut PedoniModel, counter: *mut u64, pedestrians_drawn: *mut u64) -> c_int;
+    pub fn pedoni_spawn_poisson(model: *mut PedoniModel, n_groups: u32, rates: *const PedoniSpawnRate) -> c_int;
     pub fn pedoni_count_published(model: *mut PedoniModel, count: *mut i32, rebuild_ordinal: *mut u32) -> c_int;
     pub fn pedoni_download_begin(model: *mut PedoniModel, pos_xy: *mut f32, destination: *mut u32, cap: u32) -> c_int;
     pub fn pedoni_download_end(model: *mut PedoniModel, n_out: *mut u32) -> c_int;

@@ -128,8 +128,8 @@ int pedoni_spawn(PedoniModel* model, uint32_t n, const float* pos_xy, const uint
  * (u64 number k of the stream = splitmix64(seed ^ k * 0x2545F4914F6CDD1D)): u for pedestrian j of the
  * call is u64 number counter + j (top 24 bits), the speed's two u64 are numbers counter + n + j and
  * counter + 2n + j, n = the sum of the counts — bit for bit what SpawnStream.f32 / .normal_approx return,
- * so a host-drawn and a device-drawn run are identical. The per-group counts stay with the caller (the
- * reference's Poisson draw, util.rs:78-89, is a scalar loop). Consumes 3n stream numbers.
+ * so a host-drawn and a device-drawn run are identical. The per-group counts come from the caller here;
+ * pedoni_spawn_poisson draws them on the device as well. Consumes 3n stream numbers.
  */
 typedef struct PedoniSpawnGroup {
     float p1_x, p1_y, p2_x, p2_y; /* Scenario.waypoints[origin].line */
@@ -138,6 +138,27 @@ typedef struct PedoniSpawnGroup {
 } PedoniSpawnGroup;
 int pedoni_spawn_groups(PedoniModel* model, uint32_t n_groups, const PedoniSpawnGroup* groups, uint64_t seed,
                         uint64_t counter);
+
+/*
+ * The arrivals of a tick drawn entirely ON THE DEVICE: per periodic spawn group the
+ * count = poisson(frequency / 10) of lib.rs:74 / util.rs:78-89 (Knuth's multiplication loop over fastrand::f64()),
+ * then positions and desired speeds as in pedoni_spawn_groups. How many stream numbers a Poisson draw consumes
+ * depends on its outcome, so the HANDLE owns the position in the counter stream: pedoni_spawn_stream_seek sets it
+ * (and the seed), every pedoni_spawn_poisson advances it on the device in the order of pedoni_b200/simulator.py
+ * `Simulator._spawn` (all counts, then one uniform per pedestrian, then the two speed blocks), and
+ * pedoni_spawn_stream_tell reads it back together with the number of pedestrians drawn so far (blocks). A host
+ * loop that draws from the same stream (tests: the oracle Simulator) sees bit-identical arrivals. No host-to-device
+ * copy per tick beyond the few bytes of the rate table. Must be the last spawn before pedoni_rebuild; until that
+ * rebuild pedoni_count / pedoni_download return PEDONI_ERR_STATE (only the device knows how many were drawn).
+ */
+typedef struct PedoniSpawnRate {
+    float p1_x, p1_y, p2_x, p2_y; /* Scenario.waypoints[origin].line */
+    uint32_t destination;
+    double frequency;             /* PedestrianSpawnConfig::Periodic { frequency: f64 } (scenario.rs:64), pedestrians / s */
+} PedoniSpawnRate;
+int pedoni_spawn_stream_seek(PedoniModel* model, uint64_t seed, uint64_t counter);
+int pedoni_spawn_stream_tell(PedoniModel* model, uint64_t* counter, uint64_t* pedestrians_drawn);
+int pedoni_spawn_poisson(PedoniModel* model, uint32_t n_groups, const PedoniSpawnRate* rates);
 
 /*
  * PedestrianModel::spawn_pedestrians, second half (sfm.rs:58-77): neighbor-grid rebuild.

@@ -32,8 +32,11 @@ def parse_args(argv=None):
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--log-dir", default="logs")
-    ap.add_argument("--device-spawn", action="store_true",
-                    help="draw spawn positions / desired speeds on the device (pedoni_spawn_groups); same run, no upload")
+    ap.add_argument("--device-spawn", nargs="?", const="positions", default=None, choices=["positions", "poisson"],
+                    help="draw arrivals on the device: `positions` = positions / desired speeds (pedoni_spawn_groups), "
+                         "`poisson` = the per-group Poisson counts as well (pedoni_spawn_poisson); same run, no upload")
+    ap.add_argument("--device-field", action="store_true",
+                    help="build the field maps on the GPU (pedoni_field_build_device) instead of on the host")
     ap.add_argument("--count-every", type=int, default=1, help="read the population back every N ticks (1 = reference behaviour)")
     return ap.parse_args(argv)
 
@@ -47,12 +50,13 @@ def main(argv=None) -> int:
         opts.neighbor_grid_unit = args.neighbor_unit
     scenario = Scenario.from_toml(args.scenario)                     # main.rs:54-55
     t0 = time.perf_counter()
-    field = Field.from_scenario(scenario, opts.field_grid_unit)      # lib.rs:30
+    field = Field.from_scenario(scenario, opts.field_grid_unit,      # lib.rs:30
+                                device=args.device if args.device_field else None)
     time_calc_field = time.perf_counter() - t0
     model = SocialForceModelCuda(opts, scenario, field, device=args.device,
                                  math_mode=PEDONI_MATH_FAST if args.math == "fast" else PEDONI_MATH_STRICT)
     sim = Simulator(opts, scenario, field, model, seed=args.seed, count_every=args.count_every,
-                    device_spawn=args.device_spawn)
+                    device_spawn=args.device_spawn or False)
     stop = {"now": False}
     signal.signal(signal.SIGINT, lambda *_: stop.__setitem__("now", True))   # main.rs:108
     log = StepMetricsCollection()

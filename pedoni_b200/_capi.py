@@ -59,6 +59,11 @@ class PedoniSpawnGroup(C.Structure):
                 ("destination", C.c_uint32), ("count", C.c_uint32)]
 
 
+class PedoniSpawnRate(C.Structure):
+    _fields_ = [("p1_x", C.c_float), ("p1_y", C.c_float), ("p2_x", C.c_float), ("p2_y", C.c_float),
+                ("destination", C.c_uint32), ("frequency", C.c_double)]
+
+
 class PedoniObservables(C.Structure):
     _fields_ = [("count", C.c_uint32), ("mean_speed", C.c_float), ("per_destination", C.c_uint32 * 16),
                 ("arrived", C.c_uint64 * 16), ("n_bins", C.c_uint32), ("bin_count", C.c_uint32 * 64),
@@ -87,6 +92,9 @@ SIGNATURES = {
     "pedoni_last_error": (C.c_char_p, [C.c_void_p]),
     "pedoni_spawn": (C.c_int, [C.c_void_p, C.c_uint32, c_float_p, c_u32_p, c_float_p]),
     "pedoni_spawn_groups": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PedoniSpawnGroup), C.c_uint64, C.c_uint64]),
+    "pedoni_spawn_stream_seek": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "pedoni_spawn_stream_tell": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "pedoni_spawn_poisson": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PedoniSpawnRate)]),
     "pedoni_rebuild": (C.c_int, [C.c_void_p]),
     "pedoni_step": (C.c_int, [C.c_void_p]),
     "pedoni_count": (C.c_int32, [C.c_void_p]),

@@ -82,9 +82,9 @@ __device__ __forceinline__ Located locate(const SortInput& in, uint32_t t) {
     r.a.vel = second ? in.seg[1].a.vel : in.seg[0].a.vel;
     r.a.v0 = second ? in.seg[1].a.v0 : in.seg[0].a.v0;
     r.a.dest = second ? in.seg[1].a.dest : in.seg[0].a.dest;
-    if (second) {  // the population of the appended spawns is host-known: [0, upper)
+    if (second) {  // appended spawns: [0, upper) host-known, or [0, d_range[1]) when the device drew the counts
         r.idx = t - in.prefix[1];
-        r.live = r.idx < in.seg[1].upper;
+        r.live = r.idx < (in.seg[1].d_range != nullptr ? in.seg[1].d_range[1] : in.seg[1].upper);
     } else {
         r.idx = t;
         r.live = t >= in.seg[0].d_range[0] && t < in.seg[0].d_range[1];
@@ -132,6 +132,78 @@ __global__ void __launch_bounds__(256) spawn_groups_kernel(AgentArrays out, uint
     out.pos[at + j] = make_float2(px, py);
     out.vel[at + j] = make_float2(0.0f, 0.0f);  // sfm.rs:53
     out.v0[at + j] = v0;
+    out.dest[at + j] = G.destination;
+}
+
+// ---- Poisson arrivals drawn on the device (lib.rs:70-84, util.rs:78-89) -----------------------------------------
+// The reference draws, every tick and for every periodic spawn group, count = poisson(frequency / 10) with Knuth's
+// multiplication loop over fastrand::f64() (util.rs:78-89), then a position per pedestrian. With the counts drawn
+// here too, a periodic-spawn scenario needs no host-side random numbers at all: the handle owns the position in the
+// counter stream (SpawnStreamState), because how many numbers a Poisson draw consumes depends on its outcome.
+// Stream order of one call = the order of pedoni_b200/simulator.py `Simulator._spawn`: every group's count first,
+// then one uniform per pedestrian, then the desired speeds' two blocks.
+struct SpawnRateDev {
+    float p1_x, p1_y, p2_x, p2_y;
+    uint32_t destination;
+    uint32_t max_count;     // host bound used for grid sizes; a larger draw raises kErrSpawnBound (and is clamped)
+    double exp_neg_lambda;  // exp(-frequency / 10), computed by the caller (same bits as the host-side loop)
+};
+struct SpawnStreamState {
+    unsigned long long counter;       // next unused stream number
+    unsigned long long counter_draw;  // first number of the current call's per-pedestrian draws
+    unsigned long long spawned;       // pedestrians drawn so far
+};
+
+__global__ void poisson_counts_kernel(const SpawnRateDev* __restrict__ rates, uint32_t n_groups, unsigned long long seed,
+                                      SpawnStreamState* __restrict__ st, SpawnGroupDev* __restrict__ groups,
+                                      uint32_t* __restrict__ app_range, uint32_t at, uint32_t* __restrict__ error_flag) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long ctr = st->counter;
+    uint32_t n = 0;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const SpawnRateDev R = rates[g];
+        // util.rs:78-89: y = 0; x = f64(); while x >= exp(-lambda) { x *= f64(); y += 1 }   (f64 = 53 random bits)
+        uint32_t y = 0;
+        double x = static_cast<double>(spawn_stream_u64(seed, ctr++) >> 11) * (1.0 / 9007199254740992.0);
+        while (x >= R.exp_neg_lambda) {
+            x = __dmul_rn(x, static_cast<double>(spawn_stream_u64(seed, ctr++) >> 11) * (1.0 / 9007199254740992.0));
+            ++y;
+        }
+        if (y > R.max_count) {
+            atomicOr(error_flag, kErrSpawnBound);
+            y = R.max_count;
+        }
+        groups[g] = SpawnGroupDev{R.p1_x, R.p1_y, R.p2_x, R.p2_y, R.destination, n};
+        n += y;
+    }
+    app_range[0] = 0;
+    app_range[1] = at + n;
+    st->counter_draw = ctr;
+    st->counter = ctr + 3ull * n;
+    st->spawned += n;
+}
+
+// spawn_groups_kernel with the number of pedestrians and the stream position read from the device
+__global__ void __launch_bounds__(256) spawn_groups_dev_kernel(AgentArrays out, uint32_t at, const uint32_t* __restrict__ app_range,
+                                                               const SpawnGroupDev* __restrict__ groups, uint32_t n_groups,
+                                                               unsigned long long seed, const SpawnStreamState* __restrict__ st) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = app_range[1] - at;
+    if (j >= n) return;
+    const unsigned long long counter = st->counter_draw;
+    uint32_t g = 0;
+    while (g + 1 < n_groups && groups[g + 1].first <= j) ++g;
+    const SpawnGroupDev G = groups[g];
+    const float u = static_cast<float>(spawn_stream_u64(seed, counter + j) >> 40) * (1.0f / 16777216.0f);
+    const float px = S::add(G.p1_x, S::mul(S::sub(G.p2_x, G.p1_x), u));
+    const float py = S::add(G.p1_y, S::mul(S::sub(G.p2_y, G.p1_y), u));
+    const unsigned long long a = spawn_stream_u64(seed, counter + n + j), b = spawn_stream_u64(seed, counter + 2ull * n + j);
+    const double pop = static_cast<double>(__popcll(a)) - 32.0;
+    const double tri = (static_cast<double>(b & 0xFFFFFFFFull) - static_cast<double>(b >> 32)) * (1.0 / 4294967296.0);
+    const double z = (pop + tri) * 0x1.fd5a9eebfd779p-3;
+    out.pos[at + j] = make_float2(px, py);
+    out.vel[at + j] = make_float2(0.0f, 0.0f);
+    out.v0[at + j] = S::add(1.34f, S::mul(0.26f, static_cast<float>(z)));
     out.dest[at + j] = G.destination;
 }
 

@@ -95,6 +95,13 @@ struct PedoniModel {
     AgentArrays app{};         // appended spawns, not yet rebuilt
     void* d_spawn_groups = nullptr;  // SpawnGroupDev table of pedoni_spawn_groups
     uint32_t spawn_groups_cap = 0;
+    // device-side Poisson arrivals (pedoni_spawn_poisson)
+    SpawnRateDev* d_spawn_rates = nullptr;
+    uint32_t spawn_rates_cap = 0;
+    SpawnStreamState* d_spawn_stream = nullptr;  // the handle's position in the counter stream
+    unsigned long long spawn_seed = 0;
+    uint32_t* d_app_range = nullptr;  // device [0, n): live entries of the appended spawns when the DEVICE drew the count
+    bool app_on_device = false;       // app_n is an upper bound, the count lives in d_app_range
     uint32_t app_cap = 0, app_n = 0;
     // Spawn staging: the caller's arrays (pageable or pinned) are copied into a pinned ring slot on the host and
     // travel from there, so pedoni_spawn never waits for the stream and never reads a borrowed buffer after it
@@ -404,7 +411,7 @@ SortInput make_sort_input(PedoniModel* m) {
     in.nseg = 2;
     // segment 0 is addressed by absolute array index: everything below resident_hi() (see locate())
     in.seg[0] = Segment{m->buf[m->cur], m->range(kRangeCompute), m->resident_hi()};
-    in.seg[1] = Segment{m->app, nullptr, m->app_n};
+    in.seg[1] = Segment{m->app, m->app_on_device ? m->d_app_range : nullptr, m->app_n};
     in.prefix[0] = 0;
     in.prefix[1] = m->resident_hi();
     in.prefix[2] = m->resident_hi() + m->app_n;
@@ -479,6 +486,8 @@ int check_device_error(PedoniModel* m) {
     };
     if (bits & kErrStageTimeout)
         add(PEDONI_ERR_CUDA, "force kernel: the bulk copies staging a warp's neighbour tile never completed");
+    if (bits & kErrSpawnBound)
+        add(PEDONI_ERR_CAPACITY, "a device-side Poisson draw exceeded mean + 10 sigma + 10 and was clamped");
     if (bits & kErrSortOverflow)
         add(PEDONI_ERR_CUDA, "rebuild: the overflow list of the cell slot rows ran out of entries");
     if (bits & kErrHaloTimeout)
@@ -976,7 +985,8 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_cell_count, (void*)m->d_cell_start, (void*)m->d_tile_status, (void*)m->d_tile_ticket,
                     (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_arrived, (void*)m->d_observe, (void*)m->d_distance, (void*)m->d_potential,
-                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena, m->d_spawn_groups})
+                    (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena, m->d_spawn_groups,
+                    (void*)m->d_spawn_rates, (void*)m->d_spawn_stream, (void*)m->d_app_range})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
     for (int k = 0; k < PedoniModel::kStageSlots; ++k) {
@@ -1014,6 +1024,8 @@ static int append_agents(PedoniModel* m, uint32_t n, const float* pos_xy, const 
                          const float* v0) {
     if (n == 0) return PEDONI_OK;
     if (!pos_xy || !dest || !v0) return fail(m, PEDONI_ERR_INVALID, "null agent array with n = %u", n);
+    if (m->app_on_device)
+        return fail(m, PEDONI_ERR_STATE, "pedoni_spawn_poisson must be the last spawn before pedoni_rebuild");
     if ((uint64_t)m->array_offset + m->compute_upper() + m->app_n + n + m->halo_cap > 0xFFFFFFF0ull)
         return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
     int rc = ensure_app_capacity(m, m->app_n + n);
@@ -1075,6 +1087,8 @@ int pedoni_spawn_groups(PedoniModel* m, uint32_t n_groups, const PedoniSpawnGrou
         n += groups[g].count;
     }
     if (n == 0) return PEDONI_OK;
+    if (m->app_on_device)
+        return fail(m, PEDONI_ERR_STATE, "pedoni_spawn_poisson must be the last spawn before pedoni_rebuild");
     if ((uint64_t)m->array_offset + m->compute_upper() + m->app_n + n + m->halo_cap > 0xFFFFFFF0ull)
         return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
     int rc = ensure_app_capacity(m, m->app_n + static_cast<uint32_t>(n));
@@ -1098,6 +1112,80 @@ int pedoni_spawn_groups(PedoniModel* m, uint32_t n_groups, const PedoniSpawnGrou
     return PEDONI_OK;
 }
 
+int pedoni_spawn_stream_seek(PedoniModel* m, uint64_t seed, uint64_t counter) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (!m->d_spawn_stream) {
+        CUDA_TRY(m, cudaMalloc(&m->d_spawn_stream, sizeof(SpawnStreamState)));
+        CUDA_TRY(m, cudaMalloc(&m->d_app_range, 2 * sizeof(uint32_t)));
+    }
+    const SpawnStreamState st{counter, counter, 0ull};
+    CUDA_TRY(m, cudaMemcpyAsync(m->d_spawn_stream, &st, sizeof st, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));  // `st` is a local
+    m->spawn_seed = seed;
+    return PEDONI_OK;
+}
+
+int pedoni_spawn_stream_tell(PedoniModel* m, uint64_t* counter, uint64_t* spawned) {
+    if (!m) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (!m->d_spawn_stream) return fail(m, PEDONI_ERR_STATE, "no spawn stream: call pedoni_spawn_stream_seek first");
+    SpawnStreamState st{};
+    CUDA_TRY(m, cudaMemcpyAsync(&st, m->d_spawn_stream, sizeof st, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    if (counter) *counter = st.counter;
+    if (spawned) *spawned = st.spawned;
+    return check_device_error(m);
+}
+
+int pedoni_spawn_poisson(PedoniModel* m, uint32_t n_groups, const PedoniSpawnRate* rates) {
+    if (!m || (n_groups > 0 && !rates)) return PEDONI_ERR_INVALID;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    if (!m->d_spawn_stream) return fail(m, PEDONI_ERR_STATE, "no spawn stream: call pedoni_spawn_stream_seek first");
+    if (m->app_on_device)
+        return fail(m, PEDONI_ERR_STATE, "pedoni_spawn_poisson must be the last spawn before pedoni_rebuild");
+    if (n_groups == 0) return PEDONI_OK;
+    std::vector<SpawnRateDev> dev(n_groups);
+    uint64_t bound = 0;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const double lambda = rates[g].frequency / 10.0;  // lib.rs:73
+        if (!(lambda >= 0.0) || lambda > 1.0e6) return fail(m, PEDONI_ERR_INVALID, "spawn frequency out of range");
+        // a Poisson draw above mean + 10 sigma + 10 has probability < 1e-20: the bound sizes grids and buffers
+        const uint32_t max_count = static_cast<uint32_t>(std::ceil(lambda + 10.0 * std::sqrt(lambda) + 10.0));
+        dev[g] = SpawnRateDev{rates[g].p1_x, rates[g].p1_y, rates[g].p2_x, rates[g].p2_y, rates[g].destination, max_count,
+                              std::exp(-lambda)};
+        bound += max_count;
+    }
+    if ((uint64_t)m->array_offset + m->compute_upper() + m->app_n + bound + m->halo_cap > 0xFFFFFFF0ull)
+        return fail(m, PEDONI_ERR_CAPACITY, "too many agents");
+    int rc = ensure_app_capacity(m, m->app_n + static_cast<uint32_t>(bound));
+    if (rc != PEDONI_OK) return rc;
+    if (n_groups > m->spawn_rates_cap || n_groups > m->spawn_groups_cap) {
+        cudaFree(m->d_spawn_rates);
+        cudaFree(m->d_spawn_groups);
+        m->d_spawn_rates = nullptr, m->d_spawn_groups = nullptr;
+        const uint32_t cap = std::max<uint32_t>(n_groups, 64);
+        CUDA_TRY(m, cudaMalloc(&m->d_spawn_rates, sizeof(SpawnRateDev) * cap));
+        CUDA_TRY(m, cudaMalloc(&m->d_spawn_groups, sizeof(SpawnGroupDev) * cap));
+        m->spawn_rates_cap = m->spawn_groups_cap = cap;
+    }
+    // the rate table is a few hundred bytes of pageable memory: staged by the driver before the call returns
+    CUDA_TRY(m, cudaMemcpyAsync(m->d_spawn_rates, dev.data(), sizeof(SpawnRateDev) * n_groups, cudaMemcpyHostToDevice,
+                                m->stream));
+    poisson_counts_kernel<<<1, 32, 0, m->stream>>>(m->d_spawn_rates, n_groups, m->spawn_seed, m->d_spawn_stream,
+                                                   static_cast<SpawnGroupDev*>(m->d_spawn_groups), m->d_app_range, m->app_n,
+                                                   m->d_error);
+    spawn_groups_dev_kernel<<<div_up(static_cast<uint32_t>(bound), 256), 256, 0, m->stream>>>(
+        m->app, m->app_n, m->d_app_range, static_cast<const SpawnGroupDev*>(m->d_spawn_groups), n_groups, m->spawn_seed,
+        m->d_spawn_stream);
+    m->launches += 2;
+    CUDA_TRY(m, cudaGetLastError());
+    m->app_n += static_cast<uint32_t>(bound);  // an upper bound from here on: the count lives in d_app_range
+    m->app_on_device = true;
+    m->table_valid = false;
+    return PEDONI_OK;
+}
+
 int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const uint32_t* dest, const float* vel_xy,
                         const float* v0) {
     if (!m) return PEDONI_ERR_INVALID;
@@ -1116,6 +1204,7 @@ int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const u
     m->launches += 1;
     m->owned_upper = 0;
     m->app_n = 0;
+    m->app_on_device = false;
     m->keys_fresh = false;
     m->table_valid = false;
     m->halo_pending = false;
@@ -1167,6 +1256,7 @@ static int rebuild_impl(PedoniModel* m) {
     m->rcur ^= 1;  // the layout the scan published describes buf[cur] from here on
     m->owned_upper = owned_bound(m, total);
     m->app_n = 0;
+    m->app_on_device = false;
     m->keys_fresh = false;
     m->table_valid = true;
     m->ever_rebuilt = true;
@@ -1322,6 +1412,8 @@ int pedoni_step(PedoniModel* m) {
 
 // Blocks; returns the owned range of buf[cur].
 static int sync_range(PedoniModel* m, uint32_t* begin, uint32_t* end) {
+    if (m->app_on_device)
+        return fail(m, PEDONI_ERR_STATE, "pedestrians drawn by pedoni_spawn_poisson are pending: call pedoni_rebuild first");
     int rc = sync_all(m);
     if (rc != PEDONI_OK) return rc;
     rc = check_device_error(m);

@@ -241,6 +241,7 @@ constexpr uint32_t kErrBadDestination = 1u;  // destination >= n_potential_maps 
 constexpr uint32_t kErrRowJump = 2u;         // slab handle: a pedestrian crossed >= 2 grid rows in one step
 constexpr uint32_t kErrHaloOverflow = 4u;    // slab handle: two boundary rows hold more agents than halo_capacity
 constexpr uint32_t kErrHaloTimeout = 8u;     // slab handle: a neighbour's strip did not arrive within 20 s
+constexpr uint32_t kErrSpawnBound = 64u;     // device-side Poisson draw above the host's bound (mean + 10 sigma + 10)
 constexpr uint32_t kErrSortOverflow = 32u;   // rebuild: the overflow list of the cell slots ran out (a bug: it is as long as the arrays)
 constexpr uint32_t kErrStageTimeout = 16u;   // force kernel: a warp's bulk copies never completed (a bug, not a user error)
 

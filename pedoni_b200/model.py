@@ -131,6 +131,23 @@ class SocialForceModelCuda:
                                                   C.c_uint64(counter)), self._h)
         return 3 * sum(int(g[3]) for g in groups)
 
+    def spawn_stream_seek(self, seed: int, counter: int) -> None:
+        _capi.check(self._lib.pedoni_spawn_stream_seek(self._h, C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(counter)),
+                    self._h)
+
+    def spawn_stream_tell(self):
+        """(stream position, pedestrians drawn so far) of the device-side arrivals; blocks."""
+        k, n = C.c_uint64(), C.c_uint64()
+        _capi.check(self._lib.pedoni_spawn_stream_tell(self._h, C.byref(k), C.byref(n)), self._h)
+        return k.value, n.value
+
+    def spawn_poisson(self, rates) -> None:
+        """Device-side arrivals of one tick (pedoni_spawn_poisson). rates: [(p1, p2, destination, frequency)]."""
+        arr = (_capi.PedoniSpawnRate * len(rates))(*[
+            _capi.PedoniSpawnRate(float(np.float32(p1[0])), float(np.float32(p1[1])), float(np.float32(p2[0])),
+                                  float(np.float32(p2[1])), int(d), float(f)) for p1, p2, d, f in rates])
+        _capi.check(self._lib.pedoni_spawn_poisson(self._h, len(rates), arr), self._h)
+
     def rebuild(self) -> None:
         _capi.check(self._lib.pedoni_rebuild(self._h), self._h)
 
@@ -300,6 +317,17 @@ class SlabGroup:
 
     def spawn_groups(self, groups, seed: int, counter: int) -> int:
         return [s.spawn_groups(groups, seed, counter) for s in self.slabs][0]
+
+    def spawn_stream_seek(self, seed: int, counter: int) -> None:
+        for s in self.slabs:
+            s.spawn_stream_seek(seed, counter)
+
+    def spawn_stream_tell(self):
+        return [s.spawn_stream_tell() for s in self.slabs][0]  # every slab draws the same (replicated) arrivals
+
+    def spawn_poisson(self, rates) -> None:
+        for s in self.slabs:
+            s.spawn_poisson(rates)
 
     def upload_state(self, pos, dest, vel, v0) -> None:
         for s in self.slabs:

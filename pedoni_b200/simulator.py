@@ -109,6 +109,11 @@ class Simulator:
         # draw positions and desired speeds on the device (pedoni_spawn_groups) instead of uploading them;
         # same stream numbers either way, so the two modes give identical runs
         self.device_spawn = bool(device_spawn) and hasattr(model, "spawn_groups")
+        # device_spawn="poisson": the per-group Poisson counts are drawn on the device as well
+        # (pedoni_spawn_poisson); the model then owns the stream position, and this object's `rng.k` /
+        # `spawned_total` are refreshed from it by sync_spawn_stream()
+        self.device_poisson = device_spawn == "poisson" and hasattr(model, "spawn_poisson")  # (any other true value: positions)
+        self._rates = None
         self.count_every = max(1, int(count_every))  # counting blocks; headless runs may sample it
         self._last_count = 0
         # lib.rs:37-52: "once" groups are spawned at construction
@@ -128,6 +133,16 @@ class Simulator:
         """Stream order per call: every group's count first (Poisson draws), then one uniform per pedestrian,
         group after group, then the desired speeds (sfm.rs:54, in push order) — the same on the host path
         and on the device path (pedoni_spawn_groups), so the two give bit-identical runs."""
+        if kind == "periodic" and self.device_poisson:
+            if self._rates is None:  # first periodic tick: hand the stream over to the device
+                self._rates = [(*self.scenario.waypoints[p.origin].line, p.destination, float(p.spawn.frequency))
+                               for p in self.scenario.pedestrians if p.spawn.kind == "periodic"]
+                self.model.spawn_stream_seek(int(self.rng.seed), self.rng.k)
+                self._spawned_before_device = self.spawned_total
+            if self._rates:
+                self.model.spawn_poisson(self._rates)
+            self.model.rebuild()
+            return 0
         groups = []
         for ped in self.scenario.pedestrians:
             if ped.spawn.kind != kind:
@@ -159,6 +174,12 @@ class Simulator:
             self._last_count = self.model.get_pedestrian_count()
         t2 = time.perf_counter()
         return StepMetrics(self._last_count, t1 - t0, t2 - t1, None)
+
+    def sync_spawn_stream(self) -> None:
+        """device_spawn="poisson": read the stream position and the number of arrivals back from the device (blocks)."""
+        if self.device_poisson and self._rates is not None:
+            self.rng.k, drawn = self.model.spawn_stream_tell()
+            self.spawned_total = self._spawned_before_device + drawn
 
     def list_pedestrians(self):
         return self.model.list_pedestrians()

@@ -188,3 +188,30 @@ def test_device_side_spawn_vs_oracle_simulator(name, min_seen):
                 np.testing.assert_array_equal(key(c0, cd), key(o0, od))
     assert seen >= min_seen, seen
     cu.model.close()
+
+
+@pytest.mark.parametrize("name", ["bottleneck", "random", "default", "lanes"])
+def test_device_side_poisson_arrivals_vs_oracle_simulator(name):
+    """pedoni_spawn_poisson (the remainder): the per-group Poisson counts of lib.rs:73 /
+    util.rs:78-89 are drawn on the device too, the handle owning the position in the counter stream. The oracle
+    Simulator draws the same stream on the host: populations equal every tick, order / destinations / desired speeds
+    bit-exact and positions within the strict tolerance over the first 30 ticks, and after 200 ticks both sides have
+    consumed exactly the same number of stream numbers and spawned the same number of pedestrians."""
+    cu, orc = helpers.simulator_pair(name, seed=33, math_mode=PEDONI_MATH_STRICT)
+    cu.device_spawn = cu.device_poisson = True
+    total = 0
+    for t in range(200):
+        mc, mo = cu.tick(), orc.tick()
+        assert mc.active_ped_count == mo.active_ped_count, f"{name}: population differs at tick {t}"
+        if t < 30:
+            cp, cd, cv, c0 = cu.model.download()
+            op, od, ov, o0 = orc.model.download()
+            np.testing.assert_array_equal(cd, od)
+            np.testing.assert_array_equal(bits(c0), bits(o0))
+            if len(od):
+                assert np.nanmax(np.abs(cp - op)) <= helpers.TOL_POS_ABS, f"{name}: tick {t}"
+        total = max(total, mo.active_ped_count)
+    cu.sync_spawn_stream()
+    assert cu.rng.k == orc.rng.k and cu.spawned_total == orc.spawned_total > 0, (cu.rng.k, orc.rng.k)
+    assert total > 0
+    cu.model.close()
