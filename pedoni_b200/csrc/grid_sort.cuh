@@ -540,6 +540,10 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
                 for (int chunk = 0; chunk < kChunks; ++chunk) {
                     const uint32_t c0 = warp * kCellsPerWarp + chunk * 32;
                     const uint32_t n_mine = e - s;
+                    if (__ballot_sync(kFull, n_mine != 0) == 0) {  // 32 empty cells (sparse crowds): nothing to stage
+                        if (chunk + 1 < kChunks) load_row(chunk + 1, s, e, lo, hi);
+                        continue;
+                    }
                     {
                         uint32_t m[kSlotsPerCell] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
