@@ -89,6 +89,8 @@ struct ForceParams {
     const uint32_t* d_range_hi;  // a second range for the CTAs with blockIdx.y == 1 (both edges of a slab in one launch)
     const uint32_t* d_owned;     // device [begin, end): agents this handle owns (the updates counter counts these)
     uint32_t count_upper;        // host upper bound of end - begin (grid size)
+    uint32_t cap;                // elements allocated per array (bounds checks of debug builds)
+    uint32_t table_cells;        // entries of cell_start - 1
     const uint32_t* cell_start;  // local cell table (neighbor_grid_indices, sfm.rs:22)
     GridView grid;
     FieldView field;
@@ -540,8 +542,10 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
             const bool below = y < 0, above = y >= p.grid.table_rows;
             const uint32_t ib = below ? 0u : (above ? table_end : row0 + static_cast<uint32_t>(x_start));
             const uint32_t ie = below ? 0u : (above ? table_end : row0 + static_cast<uint32_t>(x_end) + 1u);
-            r_beg[d] = __ldg(p.cell_start + ib);
-            r_end[d] = __ldg(p.cell_start + ie);
+            if (PEDONI_IN_BOUNDS(ib <= p.table_cells && ie <= p.table_cells, p.error_flag)) {
+                r_beg[d] = __ldg(p.cell_start + ib);
+                r_end[d] = __ldg(p.cell_start + ie);
+            }
         }
     }
 
@@ -557,7 +561,10 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     const uint32_t a0 = w0 & ~1u, a1 = w1 & ~1u, a2 = w2 & ~1u;
     const uint32_t n0 = ((e0 + 1u) & ~1u) - a0, n1 = ((e1 + 1u) & ~1u) - a1, n2 = ((e2 + 1u) & ~1u) - a2;
     const bool tiled = e0 >= w0 && e1 >= w1 && e2 >= w2 &&
-                       (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries);
+                       (static_cast<uint64_t>(n0) + n1 + n2) <= static_cast<uint64_t>(kTileEntries) &&
+                       // (debug builds) the staged windows, rounded outward, stay inside the arrays' cap + 2 entries
+                       PEDONI_IN_BOUNDS(static_cast<uint64_t>(a0) + n0 <= p.cap + 2ull && static_cast<uint64_t>(a1) + n1 <= p.cap + 2ull &&
+                                            static_cast<uint64_t>(a2) + n2 <= p.cap + 2ull, p.error_flag);
     if (tiled && lane == 0) {
         constexpr uint32_t kVel = sizeof(float2) * kTileAlloc;
         mbar_expect_tx(mbar_sa, (n0 + n1 + n2) * 16u);
@@ -707,6 +714,7 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     const float2 pn = make_float2(O::add(pos.x, O::mul(O::add(vn.x, vel.x), 0.05f)),
                                   O::add(pos.y, O::mul(O::add(vn.y, vel.y), 0.05f)));
 
+    if (!PEDONI_IN_BOUNDS(id < p.cap, p.error_flag)) return;
     p.out.pos[id] = pn;
     p.out.vel[id] = vn;
     p.out.v0[id] = v0;

@@ -60,6 +60,9 @@ struct SortInput {
     Segment seg[kMaxSegments];
     uint32_t prefix[kMaxSegments + 1];  // exclusive prefix of `upper`
     int nseg;
+    uint32_t cap[kMaxSegments];  // elements allocated per segment's arrays (bounds checks of debug builds)
+    uint32_t out_cap;            // elements allocated in the rebuild's output arrays
+    uint32_t* error_flag;
 };
 
 // Logical input index t -> the segment's arrays and the element index; live = false if t is outside the
@@ -228,10 +231,12 @@ struct CellSort {
     OverflowEntry* ovf;    // [ovf_cap]
     uint32_t* ovf_count;   // entries in use (reset by the sort)
     uint32_t ovf_cap;      // = capacity of the agent arrays: every pedestrian could overflow
+    uint32_t n_cells;      // cells of the local table (bounds checks of debug builds)
 };
 
 __device__ __forceinline__ void enroll(const CellSort& cs, uint32_t key, uint32_t t, uint32_t* error_flag) {
     if (key >= kKeyFirstSpecial) return;  // dropped: outside the grid, despawned, or another slab's row
+    if (!PEDONI_IN_BOUNDS(key < cs.n_cells && t < kKeyFirstSpecial, error_flag)) return;
     const uint32_t ticket = atomicAdd(cs.cell_count + key, 1u);
     if (ticket < static_cast<uint32_t>(kSlotsPerCell)) {
         cs.slots[static_cast<size_t>(key) * kSlotsPerCell + ticket] = t;
@@ -607,6 +612,11 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
                     const uint32_t r = r0 + u * kSortCtaThreads;
                     if (r < seg_hi) {
                         const Located l = locate(in, s_member[r - seg_lo]);
+                        if (!PEDONI_IN_BOUNDS(l.live && l.idx < in.cap[s_member[r - seg_lo] >= in.prefix[1] ? 1 : 0] &&
+                                                  tile_base + r < in.out_cap, in.error_flag)) {
+                            pos[u] = vel[u] = make_float2(0.f, 0.f), v0[u] = 0.f, dest[u] = 0u;
+                            continue;
+                        }
                         pos[u] = l.a.pos[l.idx];
                         vel[u] = l.a.vel[l.idx];
                         v0[u] = l.a.v0[l.idx];
@@ -616,7 +626,7 @@ __global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
 #pragma unroll
                 for (int u = 0; u < kSortUnroll; ++u) {
                     const uint32_t r = r0 + u * kSortCtaThreads;
-                    if (r < seg_hi) {
+                    if (r < seg_hi && PEDONI_IN_BOUNDS(tile_base + r < in.out_cap, in.error_flag)) {
                         const uint32_t dst = tile_base + r;
                         out.pos[dst] = pos[u];
                         out.vel[dst] = vel[u];

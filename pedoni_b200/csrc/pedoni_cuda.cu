@@ -193,7 +193,7 @@ struct PedoniModel {
     uint32_t compute_upper() const { return owned_upper + n_sides() * halo_cap; }
     // host bound above the array index of every pedestrian this handle integrates (owned + the ghost row above)
     uint32_t resident_hi() const { return array_offset + owned_upper + (has_above ? halo_cap : 0u); }
-    CellSort cell_sort() const { return CellSort{d_cell_count, d_slots, d_ovf_head, d_ovf, d_ovf_count, ovf_cap}; }
+    CellSort cell_sort() const { return CellSort{d_cell_count, d_slots, d_ovf_head, d_ovf, d_ovf_count, ovf_cap, n_cells}; }
     uint32_t* ranges(int which) const { return d_ranges + which * 2 * kNumRanges; }
     const uint32_t* range(int id) const { return ranges(rcur) + 2 * id; }
 };
@@ -415,6 +415,10 @@ SortInput make_sort_input(PedoniModel* m) {
     in.prefix[0] = 0;
     in.prefix[1] = m->resident_hi();
     in.prefix[2] = m->resident_hi() + m->app_n;
+    in.cap[0] = m->cap;
+    in.cap[1] = m->app_cap;
+    in.out_cap = m->cap;
+    in.error_flag = m->d_error;
     return in;
 }
 
@@ -435,6 +439,8 @@ void launch_force(PedoniModel* m, int range_id, uint32_t count_upper, cudaStream
     p.d_range_hi = m->range(range_id2 >= 0 ? range_id2 : range_id);
     p.d_owned = m->range(kRangeOwned);
     p.count_upper = count_upper;
+    p.cap = m->cap;
+    p.table_cells = m->n_cells;
     p.cell_start = m->d_cell_start;
     p.grid = m->grid;
     p.field = m->field;
@@ -486,6 +492,8 @@ int check_device_error(PedoniModel* m) {
     };
     if (bits & kErrStageTimeout)
         add(PEDONI_ERR_CUDA, "force kernel: the bulk copies staging a warp's neighbour tile never completed");
+    if (bits & kErrDebugBounds)
+        add(PEDONI_ERR_CUDA, "debug build: an index derived on the device left its array (the access was skipped)");
     if (bits & kErrSpawnBound)
         add(PEDONI_ERR_CAPACITY, "a device-side Poisson draw exceeded mean + 10 sigma + 10 and was clamped");
     if (bits & kErrSortOverflow)

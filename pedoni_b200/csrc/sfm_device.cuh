@@ -241,9 +241,23 @@ constexpr uint32_t kErrBadDestination = 1u;  // destination >= n_potential_maps 
 constexpr uint32_t kErrRowJump = 2u;         // slab handle: a pedestrian crossed >= 2 grid rows in one step
 constexpr uint32_t kErrHaloOverflow = 4u;    // slab handle: two boundary rows hold more agents than halo_capacity
 constexpr uint32_t kErrHaloTimeout = 8u;     // slab handle: a neighbour's strip did not arrive within 20 s
+constexpr uint32_t kErrDebugBounds = 128u;   // PEDONI_DEBUG_CHECKS builds: an index left its array (the access is skipped)
 constexpr uint32_t kErrSpawnBound = 64u;     // device-side Poisson draw above the host's bound (mean + 10 sigma + 10)
 constexpr uint32_t kErrSortOverflow = 32u;   // rebuild: the overflow list of the cell slots ran out (a bug: it is as long as the arrays)
 constexpr uint32_t kErrStageTimeout = 16u;   // force kernel: a warp's bulk copies never completed (a bug, not a user error)
+
+// Bounds checks of our own (compute-sanitizer is closed on this pool): a build with -DPEDONI_DEBUG_CHECKS=1
+// (scripts/sweep_force.py build --set debug) tests every index the kernels derive from device-side data against its
+// array's capacity, raises kErrDebugBounds and SKIPS the access; the GPU test suite is then run against that
+// library (PEDONI_CUDA_LIB). The product build compiles the checks out.
+#ifndef PEDONI_DEBUG_CHECKS
+#define PEDONI_DEBUG_CHECKS 0
+#endif
+#if PEDONI_DEBUG_CHECKS
+#define PEDONI_IN_BOUNDS(cond, error_flag) ((cond) ? true : (atomicOr((error_flag), kErrDebugBounds), false))
+#else
+#define PEDONI_IN_BOUNDS(cond, error_flag) true
+#endif
 
 // `(pos / unit).as_ivec2()` (neighbor_grid.rs:27, sfm.rs:113): IEEE divide, truncate toward zero.
 __device__ __forceinline__ int2 cell_of(float2 pos, float unit) {

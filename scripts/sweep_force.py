@@ -33,6 +33,8 @@ SORT_VARIANTS = {"base": [],  # 2 CTAs of 512 threads per SM, tiles of 4096 cell
                  "t1024_b1": ["-DPEDONI_SORT_THREADS=1024", "-DPEDONI_SORT_MIN_BLOCKS=1"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
+if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "debug":  # bounds-checked build for the test suite
+    VARIANTS = {"debug": ["-DPEDONI_DEBUG_CHECKS=1"]}
 OUT = ROOT / "build" / "variants"
 
 
