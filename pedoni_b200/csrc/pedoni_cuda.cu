@@ -1204,7 +1204,7 @@ int pedoni_upload_state(PedoniModel* m, uint32_t n, const float* pos_xy, const u
         m->halo_inflight = false;
     }
     advance_tick(m, 0);
-    // a preceding pedoni_step has already counted the (now discarded) residents into the next histogram
+    // a preceding pedoni_step has already enrolled the (now discarded) residents in the next cell table
     CUDA_TRY(m, cudaMemsetAsync(m->d_cell_count, 0, sizeof(uint32_t) * (size_t)m->n_cells, m->stream));
     CUDA_TRY(m, cudaMemsetAsync(m->d_ovf_head, 0, sizeof(uint32_t) * (size_t)m->n_cells, m->stream));
     CUDA_TRY(m, cudaMemsetAsync(m->d_ovf_count, 0, sizeof(uint32_t), m->stream));

@@ -5,7 +5,8 @@ Building it is the step BEFORE the path (lib.rs:30 builds the field, then hands 
 `PedestrianModel::new`). `Field.from_scenario` runs the host-side C++ restatement of
 `Field::from_scenario` (field.rs:220-232) in libpedoni_cuda.so (csrc/host/field_builder.cpp, SURVEY.md
 section 8 row f1) so the shipped scenario TOMLs run without the Rust side; any other builder's arrays
-(the reference's own, bench.py's closed form for the open synthetic domain) can be passed instead."""
+(the reference's own, a closed form for an open domain) can be passed instead; `from_scenario(..., device=k)` runs
+the device builder (csrc/field_device.cu), which bench.py uses for the synthetic crowd's 12 656^2 maps."""
 from __future__ import annotations
 
 import ctypes as C

@@ -8,12 +8,13 @@ through splitmix64, so any rank / the CPU oracle can regenerate identical bits f
   positions   i.i.d. uniform in [2, side - 2]^2, velocity 0 (sfm.rs:53)
   v0          N(1.34, 0.26^2) (Box-Muller) clamped to [0.5, 2.2]
   destination {0, 1} with p = 1/2; waypoints are vertical lines at x = 1 and x = side - 1
-  field       open domain, border ring only (field.rs:29-32). For an axis-aligned full-height line
-              source the reference's first-order fast marching gives potential = h * |col - col_wp|
-              and distance = h * (cells to the border ring); those closed forms are used here
-              instead of running the serial heap FMM over 1.6e8 cells (the field is an INPUT of the
-              hot path; tests/test_field_builder.py checks the closed form against the FMM builder
-              on a small domain).
+  field       open domain, border ring only (field.rs:29-32). field(device=k) builds the maps with the
+              library's device builder (what bench.py does: 1.1 s for 1.6e8 cells x 3 maps, where the
+              reference's serial heap marching takes minutes). field() is a closed form for boxes without
+              a GPU and small tests: for an axis-aligned full-height line source the first-order
+              marching gives potential = h * |col - col_wp| and distance = h * (cells to the border
+              ring); tests/test_field_builder.py checks it against the marching builder on a small
+              domain (they differ near the diagonals of the distance map, where two walls are equally far).
 """
 from __future__ import annotations
 
