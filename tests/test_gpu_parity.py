@@ -257,3 +257,53 @@ def test_two_pipelined_downloads_in_flight(corridor):
         np.testing.assert_array_equal(bits(got_pos), bits(want[k][0]))
         np.testing.assert_array_equal(got_dest, want[k][1])
     cu.close()
+
+
+def test_profile_timeline_lists_every_launch_of_a_tick(corridor):
+    """pedoni_profile_timeline: with profiling on, every launch between timer_begin and the read appears once, with
+    its stream and offsets (the two-stream timeline bench.py --timeline writes for a slab handle)."""
+    sc, field = corridor
+    cu, _ = helpers.make_pair(sc, field, math_mode=PEDONI_MATH_FAST)
+    pos, dest, vel, v0 = helpers.random_crowd(3000, sc.field.size, seed=4, margin=4.0)
+    cu.upload_state(pos, dest, vel, v0)
+    cu.rebuild()
+    cu.profile_enable(True)
+    cu.profile_reset()
+    cu.timer_begin()
+    for _ in range(3):
+        cu.step()
+        cu.rebuild()
+    ms = cu.timer_end()
+    tl = cu.profile_timeline()
+    cu.profile_enable(False)
+    assert [k for k, _, _, _ in tl] == ["force", "sort"] * 3 and all(s == "main" for _, s, _, _ in tl)
+    starts = [a for _, _, a, _ in tl]
+    assert starts == sorted(starts) and all(0 <= a <= b <= ms + 1e-3 for _, _, a, b in tl)
+    times = cu.profile_read()
+    assert times["force_launches"] == 3 and times["gather_launches"] == 3 and times["force_edge_launches"] == 0
+    cu.close()
+
+
+def test_library_pinned_buffers_carry_a_download(corridor):
+    """pedoni_host_alloc / pedoni_host_free: page-locked staging for a host that does not link the CUDA runtime (the
+    Rust shim's list_pedestrians)."""
+    import ctypes as C
+    from pedoni_b200 import _capi
+    sc, field = corridor
+    cu, _ = helpers.make_pair(sc, field)
+    pos, dest, vel, v0 = helpers.random_crowd(1500, sc.field.size, seed=6, margin=4.0)
+    cu.upload_state(pos, dest, vel, v0)
+    cu.rebuild()
+    lib = _capi.load()
+    n = cu.get_pedestrian_count()
+    p_pos, p_dest = lib.pedoni_host_alloc(8 * n), lib.pedoni_host_alloc(4 * n)
+    assert p_pos and p_dest
+    h_pos = np.ctypeslib.as_array(C.cast(p_pos, C.POINTER(C.c_float)), shape=(n, 2))
+    h_dest = np.ctypeslib.as_array(C.cast(p_dest, C.POINTER(C.c_uint32)), shape=(n,))
+    want_pos, want_dest = cu.download(vel=False, v0=False)[:2]
+    got_pos, got_dest = cu.download(vel=False, v0=False, out=(h_pos, h_dest, None, None))[:2]
+    np.testing.assert_array_equal(bits(got_pos), bits(want_pos))
+    np.testing.assert_array_equal(got_dest, want_dest)
+    lib.pedoni_host_free(p_pos)
+    lib.pedoni_host_free(p_dest)
+    cu.close()
