@@ -352,7 +352,6 @@ constexpr int kSortTile = kSortCtaThreads * kSortItems;  // cells per tile
 #ifndef PEDONI_SORT_UNROLL
 #define PEDONI_SORT_UNROLL 2  // pedestrians in flight per thread in the move pass (B200, 10 M: 2 -> 0.196 ms, 4 -> 0.207)
 #endif
-constexpr int kSortUnroll = PEDONI_SORT_UNROLL;
 #ifndef PEDONI_SORT_STAGE
 #define PEDONI_SORT_STAGE (PEDONI_SORT_THREADS * 20)  // output slots staged per round: a tile of 4096 cells holds ~8 000 pedestrians at 1 /m^2
 #endif
@@ -412,7 +411,11 @@ __device__ __forceinline__ uint32_t select_member(const CellSort& cs, uint32_t c
     return t;  // unreachable with a consistent chain
 }
 
-__global__ void __launch_bounds__(kSortCtaThreads, PEDONI_SORT_MIN_BLOCKS)
+// kMinBlocks / kSortUnroll: 2 CTAs per SM with 2 pedestrians in flight per thread is fastest on a 10 M crowd (0.188 ms
+// against 0.230 ms); a small problem (a slab of an 8-GPU run: one tile per CTA, latency only) gains from a third
+// CTA per SM, i.e. fewer cells per thread, at one pedestrian in flight (1.25 M: 39 us against 44 us). The host picks.
+template <int kMinBlocks, int kSortUnroll>
+__global__ void __launch_bounds__(kSortCtaThreads, kMinBlocks)
     sort_cells_kernel(SortInput in, CellSort cs, uint32_t n_cells, uint32_t offset, uint32_t* __restrict__ cell_start,
                       SortScratch sc, ScanLayout L, AgentArrays out) {
     // dynamic shared memory, see kSortSmemBytes

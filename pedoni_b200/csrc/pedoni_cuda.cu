@@ -929,8 +929,10 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
         CREATE_TRY(cudaGetDeviceProperties(&prop, m->device));
         m->sm_count = prop.multiProcessorCount;
     }
-    CREATE_TRY(cudaFuncSetAttribute(sort_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CREATE_TRY(cudaFuncSetAttribute(sort_cells_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(kSortSmemBytes)));
+    CREATE_TRY(cudaFuncSetAttribute(sort_cells_kernel<PEDONI_SORT_MIN_BLOCKS, PEDONI_SORT_UNROLL>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSortSmemBytes)));
     CREATE_TRY(cudaMalloc(&m->d_slots, sizeof(uint32_t) * kSlotsPerCell * ((size_t)m->n_cells + 1)));
     CREATE_TRY(cudaMalloc(&m->d_ovf_head, sizeof(uint32_t) * ((size_t)m->n_cells + 8)));
     CREATE_TRY(cudaMemsetAsync(m->d_ovf_head, 0, sizeof(uint32_t) * ((size_t)m->n_cells + 8), m->stream));
@@ -1247,17 +1249,24 @@ static int rebuild_impl(PedoniModel* m) {
                       m->has_above,     m->ranges(m->rcur ^ 1), m->h_pub_dev,               m->tick};
     {
         // one persistent kernel: prefix scan over the cells + the stable reorder of the 24-byte state
-        // Cells per thread: as few as keep every resident CTA busy with one tile (a tile's latency grows with the
-        // cells a thread owns; a 10 M crowd on one GPU takes the full 8, a slab of an 8-GPU run 5).
-        const uint32_t slots = static_cast<uint32_t>(PEDONI_SORT_MIN_BLOCKS * m->sm_count);
+        // Two instantiations: 2 CTAs per SM x 2 pedestrians in flight (large crowds) or 3 CTAs per SM x 1 (small ones,
+        // where a CTA has one tile and only latency counts). Cells per thread: as few as keep every resident CTA busy
+        // with one tile (a tile's latency grows with the cells a thread owns; a 10 M crowd on one GPU takes the full 8).
+        // (small = fewer cells than one full-size tile per CTA at 2 CTAs per SM; 2.5 M pedestrians at 1 /m^2 are not: 65 vs 63 us)
+        const bool small = m->n_cells <= 2u * static_cast<uint32_t>(m->sm_count) * kSortCtaThreads * kSortItems;
+        const uint32_t slots = static_cast<uint32_t>((small ? 3 : PEDONI_SORT_MIN_BLOCKS) * m->sm_count);
         const uint32_t items = std::min<uint32_t>(kSortItems, std::max<uint32_t>(1u, div_up(m->n_cells, slots * kSortCtaThreads)));
         const uint32_t n_tiles = div_up(m->n_cells, items * kSortCtaThreads);
         SortScratch scratch{m->d_tile_status, m->d_tile_ticket, m->d_sort_done, n_tiles, m->sort_launches & 1u, items};
         m->sort_launches += 1;
         const uint32_t ctas = std::min<uint32_t>(n_tiles, slots);
         ScopedTimer t(m, kGather, s);
-        sort_cells_kernel<<<ctas, kSortCtaThreads, kSortSmemBytes, s>>>(in, m->cell_sort(), m->n_cells, m->array_offset, m->d_cell_start,
-                                                          scratch, layout, m->buf[m->cur ^ 1]);
+        if (small)
+            sort_cells_kernel<3, 1><<<ctas, kSortCtaThreads, kSortSmemBytes, s>>>(
+                in, m->cell_sort(), m->n_cells, m->array_offset, m->d_cell_start, scratch, layout, m->buf[m->cur ^ 1]);
+        else
+            sort_cells_kernel<PEDONI_SORT_MIN_BLOCKS, PEDONI_SORT_UNROLL><<<ctas, kSortCtaThreads, kSortSmemBytes, s>>>(
+                in, m->cell_sort(), m->n_cells, m->array_offset, m->d_cell_start, scratch, layout, m->buf[m->cur ^ 1]);
         m->launches += 1;
     }
     m->cur ^= 1;

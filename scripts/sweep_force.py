@@ -25,12 +25,11 @@ VARIANTS = {  # name: extra -D flags
     "t192_b6": ["-DPEDONI_FORCE_THREADS=192", "-DPEDONI_FORCE_MIN_BLOCKS=6"],
     "t256_b4": ["-DPEDONI_FORCE_THREADS=256", "-DPEDONI_FORCE_MIN_BLOCKS=4"],
 }
-SORT_VARIANTS = {"base": [],  # 2 CTAs of 512 threads per SM, tiles of 4096 cells, 2 pedestrians in flight per thread
-                 "t256_b4": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=4"],
-                 "t256_b4_u4": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=4", "-DPEDONI_SORT_UNROLL=4"],
-                 "t128_b8": ["-DPEDONI_SORT_THREADS=128", "-DPEDONI_SORT_MIN_BLOCKS=8"],
-                 "t128_b12": ["-DPEDONI_SORT_THREADS=128", "-DPEDONI_SORT_MIN_BLOCKS=12"],
-                 "t1024_b1": ["-DPEDONI_SORT_THREADS=1024", "-DPEDONI_SORT_MIN_BLOCKS=1"]}
+SORT_VARIANTS = {"base": [],  # 2 CTAs of 512 threads per SM, 2 pedestrians in flight per thread in the move pass
+                 "b3": ["-DPEDONI_SORT_MIN_BLOCKS=3"],
+                 "b3_u1": ["-DPEDONI_SORT_MIN_BLOCKS=3", "-DPEDONI_SORT_UNROLL=1"],
+                 "t256_b6": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=6"],
+                 "t256_b8_u1": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=8", "-DPEDONI_SORT_UNROLL=1"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "debug":  # bounds-checked build for the test suite
