@@ -168,7 +168,8 @@ __global__ void poisson_counts_kernel(const SpawnRateDev* __restrict__ rates, ui
         // util.rs:78-89: y = 0; x = f64(); while x >= exp(-lambda) { x *= f64(); y += 1 }   (f64 = 53 random bits)
         uint32_t y = 0;
         double x = static_cast<double>(spawn_stream_u64(seed, ctr++) >> 11) * (1.0 / 9007199254740992.0);
-        while (x >= R.exp_neg_lambda) {
+        // (bounded: the host refuses rates whose exp(-lambda) underflows to 0, for which the reference's loop never ends)
+        while (x >= R.exp_neg_lambda && y <= R.max_count) {
             x = __dmul_rn(x, static_cast<double>(spawn_stream_u64(seed, ctr++) >> 11) * (1.0 / 9007199254740992.0));
             ++y;
         }

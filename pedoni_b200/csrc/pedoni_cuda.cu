@@ -1159,7 +1159,10 @@ int pedoni_spawn_poisson(PedoniModel* m, uint32_t n_groups, const PedoniSpawnRat
     uint64_t bound = 0;
     for (uint32_t g = 0; g < n_groups; ++g) {
         const double lambda = rates[g].frequency / 10.0;  // lib.rs:73
-        if (!(lambda >= 0.0) || lambda > 1.0e6) return fail(m, PEDONI_ERR_INVALID, "spawn frequency out of range");
+        // exp(-lambda) underflows to 0 beyond lambda ~ 745, and Knuth's loop (util.rs:82-85) then never terminates
+        if (!(lambda >= 0.0) || lambda > 700.0)
+            return fail(m, PEDONI_ERR_INVALID, "spawn frequency %g /s out of range [0, 7000]: the reference's Poisson loop "
+                                               "(util.rs:78-89) does not terminate once exp(-frequency / 10) underflows", rates[g].frequency);
         // a Poisson draw above mean + 10 sigma + 10 has probability < 1e-20: the bound sizes grids and buffers
         const uint32_t max_count = static_cast<uint32_t>(std::ceil(lambda + 10.0 * std::sqrt(lambda) + 10.0));
         dev[g] = SpawnRateDev{rates[g].p1_x, rates[g].p1_y, rates[g].p2_x, rates[g].p2_y, rates[g].destination, max_count,

@@ -215,3 +215,19 @@ def test_device_side_poisson_arrivals_vs_oracle_simulator(name):
     assert cu.rng.k == orc.rng.k and cu.spawned_total == orc.spawned_total > 0, (cu.rng.k, orc.rng.k)
     assert total > 0
     cu.model.close()
+
+
+def test_poisson_rate_beyond_the_reference_loop_is_refused():
+    """exp(-frequency / 10) underflows to 0 beyond ~7 450 pedestrians/s and Knuth's loop (util.rs:82-85) never ends:
+    pedoni_spawn_poisson refuses such a rate instead of hanging the GPU."""
+    from pedoni_b200 import PedoniError
+    sc = helpers.corridor_scenario()
+    field = helpers.oracle_field(sc)
+    cu = SocialForceModelCuda(SimulatorOptions(), sc, field)
+    cu.spawn_stream_seek(1, 0)
+    with pytest.raises(PedoniError):
+        cu.spawn_poisson([((4.0, 5.0), (4.0, 25.0), 1, 1.0e5)])
+    cu.spawn_poisson([((4.0, 5.0), (4.0, 25.0), 1, 6000.0)])  # ~600 arrivals per tick: fine
+    cu.rebuild()
+    assert 400 < cu.get_pedestrian_count() < 800
+    cu.close()
