@@ -150,6 +150,8 @@ int pedoni_spawn_groups(PedoniModel* model, uint32_t n_groups, const PedoniSpawn
  * loop that draws from the same stream (tests: the oracle Simulator) sees bit-identical arrivals. No host-to-device
  * copy per tick beyond the few bytes of the rate table. Must be the last spawn before pedoni_rebuild; until that
  * rebuild pedoni_count / pedoni_download return PEDONI_ERR_STATE (only the device knows how many were drawn).
+ * frequency must lie in [0, 7000] pedestrians / s: beyond ~7450 exp(-frequency / 10) underflows to 0 and the
+ * reference's loop (util.rs:82-85) never terminates; such a rate is refused with PEDONI_ERR_INVALID.
  */
 typedef struct PedoniSpawnRate {
     float p1_x, p1_y, p2_x, p2_y; /* Scenario.waypoints[origin].line */

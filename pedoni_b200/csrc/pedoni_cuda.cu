@@ -35,6 +35,9 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Indices of PedoniKernelTimes / PedoniLaunchRecord.kind. kGather is the sort kernel (prefix scan + reorder in one
+// launch); kHistogram / kScan / kScatter were separate launches in round 1, are never timed now and keep their slots
+// so that the struct layout of ABI 2 callers stays valid.
 enum KernelKind { kKey = 0, kHistogram, kScan, kScatter, kGather, kForce, kComm, kForceEdge, kPack, kNumKinds };
 
 struct TimedLaunch {
@@ -126,8 +129,8 @@ struct PedoniModel {
     unsigned long long* d_tile_status = nullptr;  // chained-scan status words (tick-tagged, never reset)
     uint32_t* d_tile_ticket = nullptr;            // [2], alternating per sort launch
     uint32_t n_tiles = 0;
-    // [2][kNumRanges][2], see RangeId. Double-buffered: a rebuild's scan already publishes the NEXT layout
-    // while its scatter / gather still locate the sort input through the current one.
+    // [2][kNumRanges][2], see RangeId. Double-buffered: the sort kernel's scan publishes the NEXT layout while its
+    // index and move passes still locate the sort input through the current one.
     uint32_t* d_ranges = nullptr;
     int rcur = 0;
     uint32_t* d_error = nullptr;
@@ -1615,7 +1618,7 @@ int pedoni_observe(PedoniModel* m, float y0, float y1, uint32_t n_bins, PedoniOb
     out->n_bins = n_bins;
     CUDA_TRY(m, cudaMemsetAsync(m->d_observe, 0, sizeof(ObserveOut), m->stream));
     const uint32_t upper = std::max<uint32_t>(m->owned_upper, 1);
-    const uint32_t blocks = std::min<uint32_t>(div_up(upper, 256), 148 * 8);
+    const uint32_t blocks = std::min<uint32_t>(div_up(upper, 256), static_cast<uint32_t>(m->sm_count) * 8);
     observe_kernel<<<blocks, 256, 0, m->stream>>>(m->buf[m->cur], m->range(kRangeOwned), upper, y0,
                                                   n_bins ? static_cast<float>(n_bins) / (y1 - y0) : 0.0f, n_bins,
                                                   m->d_observe);
