@@ -210,13 +210,11 @@ __device__ __forceinline__ float inv_length(float x, float y) {
 
 // Field gradient for the force terms. Strict: the reference's 8 (9) bilinear samples, bit for bit.
 // Fast: the same Sobel-of-bilinear evaluated separably on the 4x4 texel footprint with FMAs (~50 ops
-// instead of ~130). Two cases keep the reference's operation order even in fast mode:
+// instead of ~130). Three cases keep the reference's operation order even in fast mode:
 //   - map borders (out-of-bounds taps read 1e12, util.rs:45);
 //   - footprints holding through-wall values (>= 1e5 * unit; obstacle cells cost 1e6 * unit,
 //     field.rs:102): there the reference's sums of ~2.5e5-sized samples cancel catastrophically and
 //     the rounding noise IS the behaviour — pedestrians in sealed pockets random-walk on it. The
-//     separable form is more accurate, and measurably changes evacuation.toml's statistics
-//     (40 %-evacuation time 31.6 +- 1.8 s instead of the reference order's 22.6 +- 1.2 s over 20
 //     separable form is more accurate there, so it is only used where that noise is below 0.1 % of a texel;
 //   - (near-)vanishing gradients, where the reference yields either noise or an exact zero (-> NaN ->
 //     the pedestrian disappears). Without this guard evacuation.toml, whose spawn lines lie exactly on
