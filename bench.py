@@ -287,7 +287,8 @@ def run_ours(args):
     t_field = time.time()
     field = crowd.field(device=local_rank)
     t_field = time.time() - t_field
-    map_bytes = (1 + field.potential_maps.shape[0]) * field.distance_map.size * 4
+    one_map = field.distance_map.size * 4
+    map_bytes = (1 + field.potential_maps.shape[0]) * one_map
     opts = pb.SimulatorOptions()
     math_mode = pb.PEDONI_MATH_FAST if args.math == "fast" else pb.PEDONI_MATH_STRICT
     model = pb.SocialForceModelCuda(opts, sc, field, device=local_rank, math_mode=math_mode,
@@ -539,7 +540,10 @@ def run_ours(args):
         per_update, traffic_doc = traffic_record()
         use_traffic = per_update is not None and args.math == "fast" and args.density == 1.0 and \
             abs(traffic_doc.get("agents_total", 0) - args.agents) <= 0.01 * args.agents  # captured at this workload
-        compulsory = ALGO_BYTES_PER_UPDATE + map_bytes / args.agents
+        # the distance map is not fetched where the wall term is below 1e-17 m/s^2 (pedoni_wall_far_cells)
+        far_blocks, mask_blocks = model.wall_far_cells()
+        near_fraction = 1.0 - far_blocks / mask_blocks if mask_blocks else 1.0
+        compulsory = ALGO_BYTES_PER_UPDATE + (map_bytes - one_map + near_fraction * one_map) / args.agents
         out = {
             "metric": "pedestrian-updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -550,6 +554,9 @@ def run_ours(args):
                        "math_mode": args.math, "decomposition": f"{world} row slab(s)",
                        "slab_transport": model.slab_transport(),
                        "field_fetch": "texture gather (atlas)" if model.field_textures() else "global loads",
+                       "wall_term": (f"distance map not fetched in {far_blocks} of {mask_blocks} 2 m blocks: more than 8 m "
+                                     "from every obstacle, term < 1e-17 m/s^2 (pedoni_wall_far_cells; PEDONI_WALL_CUTOFF=0 "
+                                     "evaluates it everywhere)") if far_blocks else "evaluated everywhere",
                        "field_builder": f"pedoni_field_build_device (block-iterative eikonal on the GPU), {t_field:.1f} s, untimed",
                        "relax_steps_untimed": args.relax, "active_pedestrians": int(updates_all / args.steps),
                        "cpu_affinity": affinity,
@@ -582,7 +589,8 @@ def run_ours(args):
                                          "achieved": compulsory * agents_per_launch / (force_ms * 1e-3) / 1e9,
                                          "peak": peak, "unit": "GB/s",
                                          "frac": compulsory * agents_per_launch / (force_ms * 1e-3) / 1e9 / peak,
-                                         "formula": "48 + (1 + n_potential_maps) * field_ny * field_nx * 4 / N"},
+                                         "formula": "48 + (n_potential_maps + fraction of the distance map within 8 m of an "
+                                                    "obstacle or on a ridge) * field_ny * field_nx * 4 / N"},
             "kernel_ms_per_step": step_kernel_ms,
             "clocks": clocks,
         }

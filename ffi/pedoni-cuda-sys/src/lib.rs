@@ -145,6 +145,7 @@ extern "C" {
                                      obstacle_exist: *mut u8, distance_map: *mut f32, potential_maps: *mut f32,
                                      passes_out: *mut i32) -> c_int;
     pub fn pedoni_field_textures(model: *const PedoniModel) -> c_int;
+    pub fn pedoni_wall_far_cells(model: *const PedoniModel, far_cells: *mut u64, cells: *mut u64) -> c_int;
     pub fn pedoni_profile_enable(model: *mut PedoniModel, enable: i32) -> c_int;
     pub fn pedoni_profile_reset(model: *mut PedoniModel) -> c_int;
     pub fn pedoni_profile_read(model: *mut PedoniModel, out: *mut PedoniKernelTimes) -> c_int;

@@ -359,6 +359,18 @@ const char* pedoni_slab_transport(const PedoniModel* model);
  * PEDONI_FIELD_TEXTURES=0). */
 int pedoni_field_textures(const PedoniModel* model);
 
+/* Wall term far from every obstacle (PEDONI_MATH_FAST, distance-map walls; sfm.rs:188-192). The term is
+ * 10 * 0.2 * exp(-distance / 0.2): 8.5e-18 m/s^2 at 8 m, ten orders of magnitude below one ulp of a pedestrian's
+ * acceleration. At creation the handle marks the blocks of 8 x 8 distance-map texels in which, for every position
+ * whose field coordinate falls into the block, all texels the term's 4x4 footprints can touch lie inside the map,
+ * hold a distance >= 8 m, and rise or fall strictly along one axis (so that the gradient the reference normalises
+ * cannot vanish: its NaN, which removes the pedestrian, cannot occur there). In marked blocks the force kernel does
+ * not fetch the distance map at all; ridges of the map, map borders and everything closer than 8 m to an obstacle
+ * keep the full evaluation. Results differ from the unmasked fast path by < 1e-17 m/s^2 per tick (tests:
+ * bit-identical trajectories). Strict handles never skip. PEDONI_WALL_CUTOFF=0 disables the mask. Returns how many
+ * of the mask's blocks are marked (0 of n: no mask). */
+int pedoni_wall_far_cells(const PedoniModel* model, uint64_t* far_blocks, uint64_t* blocks);
+
 /* Bytes per pedestrian that pedoni_download_begin / _end move over PCIe: 8 (position) + 4 (destination), or
  * + 1 on a whole-domain handle with at most 256 potential maps — destinations then travel as bytes and
  * pedoni_download_end widens them into the caller's uint32 array on the host. Slab handles keep 4-byte

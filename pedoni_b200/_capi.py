@@ -126,6 +126,7 @@ SIGNATURES = {
     "pedoni_slab_transport": (C.c_char_p, [C.c_void_p]),
     "pedoni_halo_capacity": (C.c_int, [C.c_void_p, c_u32_p]),
     "pedoni_field_textures": (C.c_int, [C.c_void_p]),
+    "pedoni_wall_far_cells": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pedoni_download_wire_bytes": (C.c_int, [C.c_void_p]),
     "pedoni_profile_timeline": (C.c_int, [C.c_void_p, C.POINTER(PedoniLaunchRecord), C.c_uint32, c_u32_p]),
     "pedoni_host_alloc": (C.c_void_p, [C.c_size_t]),

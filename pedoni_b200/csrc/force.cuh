@@ -65,6 +65,12 @@ constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0
 #ifndef PEDONI_FAST_PAIR
 #define PEDONI_FAST_PAIR 1   // 0: PEDONI_MATH_FAST keeps the reference-order pair term (experiments)
 #endif
+#ifndef PEDONI_FAR_LOOKUP_EARLY
+#define PEDONI_FAR_LOOKUP_EARLY 1  // ask the far-from-walls mask before the potential map's gathers (B200, 10 M: 0.615 vs 0.623 ms after them)
+#endif
+#ifndef PEDONI_WALL_EARLY_ADD
+#define PEDONI_WALL_EARLY_ADD 1    // fast math: add the wall term to the acceleration before the pair loops (0.615 vs 0.619 ms)
+#endif
 constexpr int kForceThreads = PEDONI_FORCE_THREADS;
 constexpr int kForceUnroll = PEDONI_FORCE_UNROLL;
 constexpr int kForceWarps = kForceThreads / 32;
@@ -481,6 +487,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_sa, const void* src, uint3
                  : "memory");
 }
 
+// Fast math: is the wall term below 1e-17 m/s^2 at field coordinate q (FieldView::far_mask)? The mask is a few hundred
+// KB and the warps of a CTA ask for the same words: an L1 hit almost always.
+__device__ __forceinline__ bool far_from_walls_at(const FieldView& f, float2 q) {
+    const int tx = __float2int_rz(floorf(q.x)), ty = __float2int_rz(floorf(q.y));
+    if (tx < 0 || ty < 0 || tx >= f.fx || ty >= f.fy) return false;
+    const uint32_t block = static_cast<uint32_t>(ty >> kFarShift) * static_cast<uint32_t>(f.far_bw) + static_cast<uint32_t>(tx >> kFarShift);
+    return ((__ldg(f.far_mask + (block >> 5)) >> (block & 31u)) & 1u) != 0u;
+}
+
 template <Math M, bool kDistanceMap, bool kTex>
 __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_MIN_BLOCKS : PEDONI_FORCE_MIN_BLOCKS_STRICT)
     force_integrate_kernel(ForceParams p) {
@@ -603,6 +618,9 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
         const float noise_limit = 1.0e5f * p.field.unit;
         const float flat_limit2 = (8.0e-3f * p.field.unit) * (8.0e-3f * p.field.unit);
         float gx, gy, unused;
+        bool far_from_walls = false;
+        if (PEDONI_FAR_LOOKUP_EARLY && M == Math::Fast && kDistanceMap && p.field.far_mask != nullptr)
+            far_from_walls = far_from_walls_at(p.field, q);
         // dest < n_maps is guaranteed by the rebuild that admitted this agent (sort_key).
         int2 tile = make_int2(0, 0);
         if (kTex) {
@@ -615,13 +633,19 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
         e = make_float2(O::mul(gx, rlen), O::mul(gy, rlen));
         acc.x = O::add(acc.x, O::div(O::sub(O::mul(e.x, v0), vel.x), 0.5f));  // x / 0.5 == x * 2 exactly
         acc.y = O::add(acc.y, O::div(O::sub(O::mul(e.y, v0), vel.y), 0.5f));
-        if (kDistanceMap) {
+        if (!PEDONI_FAR_LOOKUP_EARLY && M == Math::Fast && kDistanceMap && p.field.far_mask != nullptr)
+            far_from_walls = far_from_walls_at(p.field, q);
+        if (kDistanceMap && !far_from_walls) {
             float dgx, dgy, distance;
             field_gradient<M, true, kTex>(p.field.distance_map, p.field.atlas, make_int2(0, 0), p.field.fy, p.field.fx, q,
                                           noise_limit, flat_limit2, dgx, dgy, distance);
             const float rl = inv_length<M>(dgx, dgy);
             const float coef = O::mul(10.0f * 0.2f, O::exp(O::div(-distance, 0.2f)));
             wall = make_float2(O::mul(coef, -O::mul(dgx, rl)), O::mul(coef, -O::mul(dgy, rl)));
+            if (M == Math::Fast && PEDONI_WALL_EARLY_ADD) {  // fast math sums in any order: two registers fewer across the pair loops
+                acc.x += wall.x;
+                acc.y += wall.y;
+            }
         }
     }
 #if PEDONI_BULK_STAGE
@@ -650,7 +674,7 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
         } else {
             pair_forces_global<M>(pos, e, p.in.pos, p.in.vel, r_beg, r_end, id, acc);
         }
-        if (kDistanceMap) {
+        if (kDistanceMap && !(M == Math::Fast && PEDONI_WALL_EARLY_ADD)) {  // the reference's order: steering, pairs, wall (sfm.rs:106-192)
             acc.x = O::add(acc.x, wall.x);
             acc.y = O::add(acc.y, wall.y);
         }

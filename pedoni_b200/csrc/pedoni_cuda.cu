@@ -64,6 +64,8 @@ struct PedoniModel {
     // fast math: the maps once more, tiled into one 2D CUDA array behind a point-sampled texture (FieldView::atlas)
     cudaArray_t field_atlas = nullptr;
     bool field_tex = false;
+    uint32_t* d_far_mask = nullptr;  // FieldView::far_mask
+    unsigned long long far_cells = 0, far_blocks_total = 0;  // marked / all blocks of the mask
     float* d_edges = nullptr;
     int n_obstacles = 0;
     uint32_t n_cells = 0;  // local table cells
@@ -757,6 +759,83 @@ void build_field_textures(PedoniModel* m) {
     m->field_tex = true;
 }
 
+// ---- far-from-walls mask (fast math, distance-map walls) -----------------------------------------------
+// The wall term is 10 * 0.2 * exp(-distance / 0.2) * direction (sfm.rs:188-192): at 8 m it is 2 e^-40 = 8.5e-18 m/s^2,
+// ten orders of magnitude below one ulp of any acceleration a pedestrian has. One bit per block of 8 x 8 texels of
+// the distance map says: for EVERY position whose field coordinate (pos / unit - 0.5, field.rs:243) floors into the
+// block, all texels the wall term's 4x4 footprints can touch (floor - 1 .. floor + 2, plus one texel of margin) lie
+// inside the map and hold a distance >= kWallCutoff, and the map is strictly monotone along x or along y over that
+// region (steps of one sign, each beyond 1e-3 * unit) — then the Sobel gradient cannot vanish, so the reference's
+// `normalize()` cannot produce the NaN that removes a pedestrian (edge semantics), and
+// skipping the term changes the acceleration by less than 1e-17. Ridges of the distance map (corridor mid-lines, the
+// diagonals of an open square), map borders and anything NaN keep the full evaluation.
+constexpr float kWallCutoff = 8.0f;  // metres
+
+__global__ void __launch_bounds__(256) far_mask_kernel(FieldView f, int blocks_y, uint32_t* __restrict__ mask,
+                                                       unsigned long long* __restrict__ n_far) {
+    const uint32_t block = blockIdx.x * blockDim.x + threadIdx.x;
+    if (block >= static_cast<uint32_t>(f.far_bw) * static_cast<uint32_t>(blocks_y)) return;
+    const int bx = static_cast<int>(block % static_cast<uint32_t>(f.far_bw)), by = static_cast<int>(block / static_cast<uint32_t>(f.far_bw));
+    constexpr int kB = 1 << kFarShift;
+    const int x0 = bx * kB - 2, x1 = bx * kB + kB - 1 + 3;
+    const int y0 = by * kB - 2, y1 = by * kB + kB - 1 + 3;
+    if (x0 < 0 || y0 < 0 || x1 >= f.fx || y1 >= f.fy) return;  // map border: out-of-bounds taps read 1e12 (util.rs:45)
+    const float eps = 1.0e-3f * f.unit;
+    bool far = true, up_x = true, down_x = true, up_y = true, down_y = true;
+    for (int y = y0; y <= y1; ++y) {
+        const float* row = f.distance_map + static_cast<size_t>(y) * f.fx;
+        for (int x = x0; x <= x1; ++x) {
+            const float v = row[x];
+            far = far && v >= kWallCutoff;  // false for NaN
+            if (x < x1) {
+                const float d = row[x + 1] - v;
+                up_x = up_x && d > eps;
+                down_x = down_x && d < -eps;
+            }
+            if (y < y1) {
+                const float d = row[x + f.fx] - v;
+                up_y = up_y && d > eps;
+                down_y = down_y && d < -eps;
+            }
+        }
+    }
+    if (far && (up_x || down_x || up_y || down_y)) {
+        atomicOr(mask + (block >> 5), 1u << (block & 31u));
+        atomicAdd(n_far, 1ull);
+    }
+}
+
+// Any failure leaves the handle without a mask (every wall term evaluated): an optimisation, not a requirement.
+void build_far_mask(PedoniModel* m) {
+    const char* env = std::getenv("PEDONI_WALL_CUTOFF");
+    if (env && env[0] == '0') return;
+    constexpr int kB = 1 << kFarShift;
+    const int bw = (m->field.fx + kB - 1) / kB, bh = (m->field.fy + kB - 1) / kB;
+    const uint32_t blocks = static_cast<uint32_t>(bw) * static_cast<uint32_t>(bh);
+    const size_t words = (static_cast<size_t>(blocks) + 31) / 32;
+    m->field.far_bw = bw;
+    m->far_blocks_total = blocks;
+    unsigned long long* d_n = nullptr;
+    bool ok = cudaMalloc(&m->d_far_mask, words * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&d_n, sizeof(unsigned long long)) == cudaSuccess;
+    if (ok) {
+        cudaMemsetAsync(m->d_far_mask, 0, words * sizeof(uint32_t), m->stream);
+        cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), m->stream);
+        far_mask_kernel<<<div_up(blocks, 256), 256, 0, m->stream>>>(m->field, bh, m->d_far_mask, d_n);
+        ok = cudaMemcpyAsync(&m->far_cells, d_n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess &&
+             cudaStreamSynchronize(m->stream) == cudaSuccess;
+    }
+    cudaFree(d_n);
+    if (!ok || m->far_cells == 0) {  // nothing to skip: keep the kernel off the extra load
+        (void)cudaGetLastError();
+        cudaFree(m->d_far_mask);
+        m->d_far_mask = nullptr;
+        m->far_cells = 0;
+        return;
+    }
+    m->field.far_mask = m->d_far_mask;
+}
+
 }  // namespace
 
 // ===================================================================================================
@@ -914,6 +993,7 @@ int pedoni_create(const PedoniConfig* c, PedoniModel** out) {
     m->field.distance_map = m->d_distance;
     m->field.potential_maps = m->d_potential;
     if (m->math_mode == PEDONI_MATH_FAST) build_field_textures(m);
+    if (m->math_mode == PEDONI_MATH_FAST && m->use_distance_map) build_far_mask(m);
 
     m->n_obstacles = c->n_obstacles;
     if (!m->use_distance_map && m->n_obstacles > 0) {
@@ -999,7 +1079,7 @@ void pedoni_destroy(PedoniModel* m) {
                     (void*)m->d_ranges,
                     (void*)m->d_error, (void*)m->d_updates, (void*)m->d_arrived, (void*)m->d_observe, (void*)m->d_distance, (void*)m->d_potential,
                     (void*)m->d_edges, (void*)m->d_send_dn, (void*)m->d_send_up, (void*)m->d_arena, m->d_spawn_groups,
-                    (void*)m->d_spawn_rates, (void*)m->d_spawn_stream, (void*)m->d_app_range})
+                    (void*)m->d_spawn_rates, (void*)m->d_spawn_stream, (void*)m->d_app_range, (void*)m->d_far_mask})
         cudaFree(p);
     if (m->h_pub) cudaFreeHost(m->h_pub);
     for (int k = 0; k < PedoniModel::kStageSlots; ++k) {
@@ -1795,6 +1875,12 @@ const char* pedoni_slab_transport(const PedoniModel* m) {
     }
 }
 int pedoni_field_textures(const PedoniModel* m) { return m && m->field_tex ? 1 : 0; }
+int pedoni_wall_far_cells(const PedoniModel* m, uint64_t* far_cells, uint64_t* cells) {
+    if (!m || !far_cells || !cells) return PEDONI_ERR_INVALID;
+    *far_cells = m->far_cells;
+    *cells = m->far_blocks_total;
+    return PEDONI_OK;
+}
 
 int pedoni_halo_capacity(const PedoniModel* m, uint32_t* halo_capacity) {
     if (!m || !halo_capacity) return PEDONI_ERR_INVALID;

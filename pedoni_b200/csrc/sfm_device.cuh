@@ -88,6 +88,7 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
 // tap reads 1e12 (util.rs:45,53-56). No texture hardware: the reference's own OpenCL path uses it
 // (sfm_gpu.cl:4-5) and diverges from the CPU model (9-bit weights, clamp addressing).
 // ------------------------------------------------------------------------------------------------
+constexpr int kFarShift = 3;  // 8 x 8 texels (2 m x 2 m at the default field unit) per bit of FieldView::far_mask
 struct FieldView {
     float unit;
     float inv_unit;  // 1 / unit when unit is a power of two (then x * inv_unit == x / unit bit for bit), else 0
@@ -103,6 +104,13 @@ struct FieldView {
     cudaTextureObject_t atlas;
     int atlas_tiles_x;  // a power of two: tile t sits at ((t & (tiles_x - 1)) * fx, (t >> atlas_shift) * fy)
     int atlas_shift;    // log2(atlas_tiles_x)
+    // Fast math, distance-map walls: one bit per block of kFarBlock x kFarBlock texels, set where the wall term
+    // (10 * 0.2 * exp(-distance / 0.2), sfm.rs:191) is below 1e-17 m/s^2 for every position whose field coordinate
+    // floors into the block AND its direction cannot be NaN there (far_mask_kernel in pedoni_cuda.cu). The force
+    // kernel skips the distance map's footprint for such positions. nullptr: no mask (strict handles, segment
+    // walls, PEDONI_WALL_CUTOFF=0). far_bw: blocks per row of the mask.
+    int far_bw;
+    const uint32_t* __restrict__ far_mask;
 };
 
 __device__ __forceinline__ float field_tap(const float* __restrict__ g, int ny, int nx, int x, int y) {

@@ -277,6 +277,13 @@ class SocialForceModelCuda:
         """True if the force kernel fetches the field maps with texture gathers (fast math only)."""
         return bool(self._lib.pedoni_field_textures(self._h))
 
+    def wall_far_cells(self):
+        """(marked, total) blocks of 8 x 8 distance-map texels in which the fast-math force kernel skips the wall
+        term (pedoni_wall_far_cells: more than 8 m from every obstacle, no ridge of the distance map)."""
+        far, total = C.c_uint64(), C.c_uint64()
+        _capi.check(self._lib.pedoni_wall_far_cells(self._h, C.byref(far), C.byref(total)), self._h)
+        return int(far.value), int(total.value)
+
     def halo_capacity(self) -> int:
         h = C.c_uint32()
         _capi.check(self._lib.pedoni_halo_capacity(self._h, C.byref(h)), self._h)

@@ -32,6 +32,12 @@ SORT_VARIANTS = {"base": [],  # 2 CTAs of 512 threads per SM, 2 pedestrians in f
                  "t256_b8_u1": ["-DPEDONI_SORT_THREADS=256", "-DPEDONI_SORT_MIN_BLOCKS=8", "-DPEDONI_SORT_UNROLL=1"]}
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "sort":
     VARIANTS = SORT_VARIANTS
+WALL_VARIANTS = {"late_add": ["-DPEDONI_FAR_LOOKUP_EARLY=0"],
+                 "late_noadd": ["-DPEDONI_FAR_LOOKUP_EARLY=0", "-DPEDONI_WALL_EARLY_ADD=0"],
+                 "early_add": [],  # the defaults
+                 "early_noadd": ["-DPEDONI_WALL_EARLY_ADD=0"]}
+if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "wall":  # far-from-walls mask: where to ask, when to add
+    VARIANTS = WALL_VARIANTS
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "debug":  # bounds-checked build for the test suite
     VARIANTS = {"debug": ["-DPEDONI_DEBUG_CHECKS=1"]}
 OUT = ROOT / "build" / "variants"

@@ -233,6 +233,47 @@ def test_texture_gather_path_is_bit_identical_to_loads(corridor, monkeypatch):
     strict.close()
 
 
+def test_wall_far_mask_changes_nothing(monkeypatch):
+    """Fast math skips the wall term (sfm.rs:188-192) in cells that pedoni_wall_far_cells marks: more than 8 m from
+    every obstacle (the term is below 1e-17 m/s^2 there) and off the ridges of the distance map (where the reference's
+    normalize() may yield NaN). Twenty ticks of an open 144 m square agree with a handle that evaluates every wall
+    term (PEDONI_WALL_CUTOFF=0) bit for bit (up to two last-place flips allowed: 1e-17 can decide a rounding)."""
+    from pedoni_b200 import SocialForceModelCuda
+    from pedoni_b200.synthetic import SyntheticCrowd
+    crowd = SyntheticCrowd(20000)
+    sc, field = crowd.scenario(), crowd.field()
+    pos, dest, vel, v0 = crowd.agents()
+    outs, marked = [], []
+    for knob in ("1", "0"):
+        monkeypatch.setenv("PEDONI_WALL_CUTOFF", knob)
+        cu = SocialForceModelCuda(SimulatorOptions(), sc, field, math_mode=PEDONI_MATH_FAST)
+        marked.append(cu.wall_far_cells())
+        cu.upload_state(pos, dest, vel, v0)
+        for _ in range(20):
+            cu.rebuild()
+            cu.step()
+        outs.append(cu.download())
+        cu.close()
+    (far, total), (far_off, _) = marked
+    # 144 m square, 8 m cut-off + footprint margin, minus the four diagonal ridges of min(x, y, W - x, H - y)
+    assert far_off == 0 and 0.45 * total < far < 0.8 * total, marked
+    for a, b in zip(*outs):
+        assert a.shape == b.shape
+        differ = bits(a) != bits(b)
+        assert differ.sum() <= 2 and (differ.sum() == 0 or np.abs(a - b).max() <= 1e-6), int(differ.sum())
+    monkeypatch.setenv("PEDONI_WALL_CUTOFF", "1")
+    # a 16 m wide corridor (walls 10 m apart) has no far blocks at all, and strict handles never carry a mask
+    sc2 = helpers.corridor_scenario(size=(60.0, 16.0))
+    f2 = helpers.oracle_field(sc2)
+    for mode in (PEDONI_MATH_FAST, PEDONI_MATH_STRICT):
+        cu = SocialForceModelCuda(SimulatorOptions(), sc2, f2, math_mode=mode)
+        assert cu.wall_far_cells()[0] == 0
+        cu.close()
+    strict = SocialForceModelCuda(SimulatorOptions(), sc, field, math_mode=PEDONI_MATH_STRICT)
+    assert strict.wall_far_cells()[0] == 0
+    strict.close()
+
+
 def test_two_pipelined_downloads_in_flight(corridor):
     """begin k, begin k+1, end k, end k+1: _end completes the oldest; a third begin is refused."""
     import torch
