@@ -71,6 +71,9 @@ constexpr int kEdgeFloats = 24;                   // per obstacle: 4 x (l0.x, l0
 #ifndef PEDONI_WALL_EARLY_ADD
 #define PEDONI_WALL_EARLY_ADD 1    // fast math: add the wall term to the acceleration before the pair loops (0.615 vs 0.619 ms)
 #endif
+#ifndef PEDONI_PREFETCH_AHEAD
+#define PEDONI_PREFETCH_AHEAD 0  // pedestrians ahead whose state a warp pulls into L2 (0 = off; experiments)
+#endif
 constexpr int kForceThreads = PEDONI_FORCE_THREADS;
 constexpr int kForceUnroll = PEDONI_FORCE_UNROLL;
 constexpr int kForceWarps = kForceThreads / 32;
@@ -526,6 +529,21 @@ __global__ void __launch_bounds__(kForceThreads, M == Math::Fast ? PEDONI_FORCE_
     if (PEDONI_BULK_STAGE) {
         if (lane == 0) mbar_init(mbar_sa, 1);
         __syncwarp();
+    }
+
+    if (PEDONI_PREFETCH_AHEAD > 0) {
+        // the state of the warp that runs about one wave later: DRAM -> L2 now, so that its first loads are L2 hits
+        const uint32_t ahead = warp_first + static_cast<uint32_t>(PEDONI_PREFETCH_AHEAD);
+        if (ahead + 32u <= end) {
+            if ((lane & 15) == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in.pos + ahead + lane));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in.vel + ahead + lane));
+            }
+            if (lane == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in.v0 + ahead));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in.dest + ahead));
+            }
+        }
     }
 
     float2 pos = make_float2(0.f, 0.f), vel = pos, e = pos, acc = pos;

@@ -36,6 +36,10 @@ WALL_VARIANTS = {"late_add": ["-DPEDONI_FAR_LOOKUP_EARLY=0"],
                  "late_noadd": ["-DPEDONI_FAR_LOOKUP_EARLY=0", "-DPEDONI_WALL_EARLY_ADD=0"],
                  "early_add": [],  # the defaults
                  "early_noadd": ["-DPEDONI_WALL_EARLY_ADD=0"]}
+PREFETCH_VARIANTS = {"base": [], "ahead_1wave": ["-DPEDONI_PREFETCH_AHEAD=170496"], "ahead_2waves": ["-DPEDONI_PREFETCH_AHEAD=340992"],
+                     "ahead_half": ["-DPEDONI_PREFETCH_AHEAD=85248"]}
+if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "prefetch":  # L2 prefetch of a later warp's state
+    VARIANTS = PREFETCH_VARIANTS
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "wall":  # far-from-walls mask: where to ask, when to add
     VARIANTS = WALL_VARIANTS
 if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "debug":  # bounds-checked build for the test suite
